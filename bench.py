@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — scan-matches/sec of the B200 scan matcher (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): batches of 4096 independent 1081-point synthetic scans matched
+against a frozen 3-level 2048^2 map (0.05 m), full MapRepMultiMap::matchData each (4+4+6 = 14
+H/dTr evaluations).  A "step" = one batch.  With N GPUs every rank matches its own 4096 scans per
+step against its replica of the map (weak scaling; the map is built on rank 0 and replicated with
+one NCCL broadcast, no collective on the data path).
+
+  value     whole-job matches/s with inputs resident in HBM (one kernel launch per step per rank)
+  e2e       the same through the host-buffer C-ABI call hsb_match_batch: pinned host scans/hints
+            copied to the device and poses copied back inside the timed region, every step
+  roofline  algorithmic bytes of the match kernel (24 B per endpoint-evaluation)
+            over its measured duration, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own CPU matcher (oracle/_ref, else the C port) on this box's cores
+
+`--impl reference` times only that CPU arm and prints it as the main line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MAP_SIZE = 2048
+LEVELS = 3
+RES = 0.05
+BATCH = 4096
+N_PTS = 1081
+EVALS = 14
+BYTES_PER_MATCH = N_PTS * 24 * EVALS  # 363 216 B
+METRIC = "scan-matches/sec (1081-pt scans, 3-level map)"
+WORKLOAD = "batch of 4096 independent 1081-pt synthetic scans, 3-level 2048^2 map, full matchData"
+
+
+# ---------------------------------------------------------------------------------------------
+def make_workload(seed: int, batch: int):
+    """Seeded scans + hints for one rank."""
+    from hector_slam_b200 import synth
+
+    world = synth.World.for_map_size(MAP_SIZE)
+    rng = np.random.default_rng(1000 + seed)
+    poses = world.sample_free_poses(batch, rng)
+    pts, offs = synth.make_scan_batch(world, poses, noise_seed=7 + seed)
+    hints = synth.perturb_hints(poses, seed=1 + seed, dxy=0.1, dpsi=0.05)
+    assert pts.shape[0] == batch * N_PTS
+    return world, poses, pts, offs, hints
+
+
+def build_map_on_gpu(rep, world):
+    """Mapping with known poses through the product path (matchData fills the coarse containers,
+    updateByScan writes every level) — same recipe as oracle.pyoracle.build_map_known_poses."""
+    from hector_slam_b200 import synth
+
+    rng = np.random.default_rng(11)
+    for p in world.mapping_poses():
+        scan = synth.make_scan(world, p, rng)
+        p32 = p.astype(np.float32)
+        rep.matchData(p32, scan)
+        rep.updateByScan(scan, p32)
+        rep.onMapUpdated()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(world, pts, offs, hints, planes, steps: int, warmup: int, max_seconds: float = 20.0):
+    """Time the reference's CPU matcher (oracle/_ref when present, else the C port) with all host
+    threads on a bounded sample of the workload. Returns (matches_per_s, info)."""
+    from oracle import pyoracle
+
+    if not pyoracle.available("port"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
+    kind = "reference" if pyoracle.available("reference") else "port"
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    orc = pyoracle.Oracle(kind, RES, MAP_SIZE, LEVELS)
+    orc.set_update_factors(0.4, 0.9)
+    for l in range(LEVELS):
+        orc.set_logodds(l, planes[l])
+    B = hints.shape[0]
+    # calibrate on a small single-thread run, then size a step to ~max_seconds/(steps+warmup)
+    n0 = min(B, 64)
+    _, _, s0 = orc.match_batch(hints[:n0], pts[: offs[n0]], offs[: n0 + 1], nthreads=1, want_cov=True)
+    per_match = s0 / n0
+    budget = max_seconds / max(1, steps + warmup)
+    n_step = int(min(B, max(threads * 8, budget * threads / per_match)))
+    sub_pts, sub_offs, sub_hints = pts[: offs[n_step]], offs[: n_step + 1], hints[:n_step]
+    secs = []
+    for it in range(warmup + steps):
+        _, _, s = orc.match_batch(sub_hints, sub_pts, sub_offs, nthreads=threads)
+        if it >= warmup:
+            secs.append(s)
+    orc.close()
+    total = float(np.sum(secs))
+    value = n_step * len(secs) / total
+    info = {"value": value, "unit": "scan-matches/s", "cores": threads, "kind": kind,
+            "sample": f"{len(secs)} x {n_step} of the {B} scans, {threads} threads (one private matcher each), "
+                      f"single-thread {1.0 / per_match:.0f} matches/s",
+            "host_cpus": cores, "ms_per_step": 1e3 * total / len(secs), "n_step": n_step}
+    return value, info
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "tex"])
+    ap.add_argument("--sweep", action="store_true", help="print throughput for launch shapes / gather modes and exit")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nbuf", type=int, default=8, help="distinct input batches cycled through (inputs > L2)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import pyoracle  # noqa: F401  (bench.py's reference arm may execute oracle/)
+
+        world, poses, pts, offs, hints = make_workload(0, args.batch)
+        # the same map recipe on the CPU side
+        kind = "reference" if pyoracle.available("reference") else "port"
+        if not pyoracle.available("port"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
+        orc = pyoracle.Oracle(kind, RES, MAP_SIZE, LEVELS)
+        orc.set_update_factors(0.4, 0.9)
+        pyoracle.build_map_known_poses(orc, world)
+        planes = [orc.get_logodds(l) for l in range(LEVELS)]
+        orc.close()
+        value, info = cpu_reference_run(world, pts, offs, hints, planes, args.steps, args.warmup)
+        line = {"metric": METRIC, "value": value, "unit": "scan-matches/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": {"workload": WORKLOAD, "map": f"{MAP_SIZE}^2 x {LEVELS} levels @ {RES} m",
+                           "evaluations_per_match": EVALS, "step": f"{info['n_step']} scans on the host cores"},
+                "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": value, "unit": "scan-matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from hector_slam_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    gather = {"auto": capi.GATHER_AUTO, "ldg": capi.GATHER_LDG, "tex": capi.GATHER_TEX}[args.gather]
+    rep = capi.MapRepB200(RES, MAP_SIZE, levels=LEVELS, device=local_rank, update_factor_free=0.4,
+                          update_factor_occupied=0.9, gather_mode=gather)
+
+    world, poses, pts, offs, hints = make_workload(rank, args.batch)
+    B = args.batch
+
+    # ---- map: built once on rank 0 through the product path, replicated with one NCCL broadcast
+    if rank == 0:
+        build_map_on_gpu(rep, world)
+    planes_dev = []
+    for l in range(LEVELS):
+        sx, sy, _ = rep.level_info(l)
+
+        class _Wrap:  # zero-copy view of the handle's log-odds plane for torch / NCCL
+            __cuda_array_interface__ = {"shape": (sy, sx), "typestr": "<f4", "data": (rep.level_logodds_device_ptr(l), False),
+                                        "version": 2}
+
+        planes_dev.append(torch.as_tensor(_Wrap(), device=dev))
+    if world_size > 1:
+        for l in range(LEVELS):
+            dist.broadcast(planes_dev[l], src=0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            for l in range(LEVELS):
+                rep.refresh_level(l, 0)
+        torch.cuda.synchronize()
+    planes_host = [p.cpu().numpy() for p in planes_dev] if rank == 0 else None
+
+    # ---- device-resident inputs: nbuf distinct copies so that a step's inputs are not L2-warm
+    nbuf = max(1, args.nbuf)
+    d_pts = [torch.from_numpy(pts).to(dev).clone() for _ in range(nbuf)]
+    d_hints = [torch.from_numpy(hints).to(dev).clone() for _ in range(nbuf)]
+    d_offs = torch.from_numpy(offs).to(dev)
+    d_poses = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    d_cov = torch.empty((B, 9), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device(i):
+        k = i % nbuf
+        rep.match_batch_device(B, d_hints[k].data_ptr(), d_pts[k].data_ptr(), d_offs.data_ptr(), 0, N_PTS,
+                               d_poses.data_ptr(), d_cov.data_ptr(), stream)
+
+    if args.sweep:
+        for mode in ("ldg", "tex"):
+            r2 = capi.MapRepB200(RES, MAP_SIZE, levels=LEVELS, device=local_rank, update_factor_free=0.4,
+                                 update_factor_occupied=0.9, gather_mode={"ldg": 1, "tex": 2}[mode])
+            for l in range(LEVELS):
+                r2.upload_level(l, planes_host[l])
+            for stage in (1, 0):
+                for (w, g) in ((1, 1), (1, 2), (1, 4), (1, 8), (2, 1), (2, 2), (2, 4), (4, 1), (4, 2), (8, 1), (16, 1)):
+                    r2.set_tuning(warps_per_scan=w, scans_per_block=g, stage_smem=stage)
+                    for i in range(3):
+                        r2.match_batch_device(B, d_hints[0].data_ptr(), d_pts[0].data_ptr(), d_offs.data_ptr(), 0, N_PTS,
+                                              d_poses.data_ptr(), d_cov.data_ptr(), stream)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for i in range(10):
+                        r2.match_batch_device(B, d_hints[i % nbuf].data_ptr(), d_pts[i % nbuf].data_ptr(), d_offs.data_ptr(),
+                                              0, N_PTS, d_poses.data_ptr(), d_cov.data_ptr(), stream)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / 10
+                    print(f"sweep mode={mode} stage={stage} W={w} G={g}: {ms:.3f} ms/step  {B / ms * 1e3 / 1e6:.2f} M matches/s",
+                          flush=True)
+            r2.close()
+        return
+
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = rep.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step_device(args.warmup + i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    if world_size > 1:
+        dist.barrier()
+    launches = rep.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(np.sum(step_ms))
+    # the K steps are back to back on one stream; also take the first-start -> last-stop span
+    span_ms = ev[0][0].elapsed_time(ev[-1][1])
+    t = torch.tensor([span_ms], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    span_ms_max = float(t.item())
+    value = world_size * B * args.steps / (span_ms_max * 1e-3)
+    kernel_ms = total_ms / args.steps
+
+    # ---- timed region 2: end to end through hsb_match_batch with pinned host buffers -----------
+    h_pts = torch.from_numpy(pts).pin_memory()
+    h_hints = torch.from_numpy(hints).pin_memory()
+    h_offs = torch.from_numpy(offs)
+    h_poses = torch.empty((B, 3), dtype=torch.float32).pin_memory()
+    h_cov = torch.empty((B, 9), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        rep.match_batch(h_hints, h_pts, h_offs.numpy(), want_cov=True, out_poses=h_poses, out_cov=h_cov)
+
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    launches_e0 = rep.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e2e_launches = rep.launch_count - launches_e0
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world_size * B * args.steps / float(te.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # parity spot check of the e2e result against the device-resident path (same inputs)
+    step_device(0) if nbuf == 1 else rep.match_batch_device(B, d_hints[0].data_ptr(), d_pts[0].data_ptr(),
+                                                           d_offs.data_ptr(), 0, N_PTS, d_poses.data_ptr(),
+                                                           d_cov.data_ptr(), stream)
+    torch.cuda.synchronize()
+    same = float((d_poses.cpu() - h_poses).abs().max())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = BYTES_PER_MATCH * B / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "scan-matches/s", "n_gpus": world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": span_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "map": f"{MAP_SIZE}^2 x {LEVELS} levels @ {RES} m", "batch_per_gpu": B,
+                       "evaluations_per_match": EVALS, "gather": {1: "ldg", 2: "tex"}[rep.gather_mode],
+                       "cache": f"inputs larger than L2: {nbuf} distinct input batches cycled "
+                                f"({nbuf * pts.nbytes / 1e6:.0f} MB of endpoints); the frozen map is reused by design",
+                       "map_replication": "rank 0 builds, one NCCL broadcast" if world_size > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "scan-matches/s",
+                    "h2d_bytes_per_step": int(pts.nbytes + hints.nbytes + offs.nbytes),
+                    "d2h_bytes_per_step": int(B * 12 + B * 36), "launches": int(e2e_launches),
+                    "max_abs_diff_vs_device_path": same},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "hsb::match_kernel",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_MATCH * B},
+            "clocks": clocks,
+            "wall_ms_per_step": 1e3 * (t_wall1 - t_wall0) / args.steps,
+        }
+        if not args.no_cpu_baseline and world_size == 1:
+            _, info = cpu_reference_run(world, pts, offs, hints, planes_host, steps=3, warmup=1, max_seconds=16.0)
+            line["cpu_baseline"] = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    rep.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,308 @@
+"""ctypes binding of the C-ABI in include/hector_slam_b200.h (lib/libhsb200.so).
+
+Python here is plumbing only (tests, bench.py, multi-GPU launcher): device memory and streams may
+come from torch, everything that computes goes through the C-ABI into the CUDA kernels.  There is
+no CPU fallback — if the library is missing or no GPU is visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libhsb200.so")
+HSB_MAX_LEVELS = 8
+
+GATHER_AUTO, GATHER_LDG, GATHER_TEX = 0, 1, 2
+
+# every symbol include/hector_slam_b200.h declares (tests check the .so exports them all)
+EXPORTED = [
+    "hsb_create", "hsb_destroy", "hsb_reset", "hsb_set_update_factor_free", "hsb_set_update_factor_occupied",
+    "hsb_get_logodds_increments", "hsb_get_scale_to_map", "hsb_get_map_levels", "hsb_get_level_info",
+    "hsb_map_coords_pose", "hsb_world_coords_pose", "hsb_match_data", "hsb_match_batch", "hsb_match_batch_device",
+    "hsb_hessian_derivs", "hsb_update_by_scan", "hsb_update_level_by_scan", "hsb_on_map_updated",
+    "hsb_upload_level", "hsb_download_level", "hsb_download_prob", "hsb_level_logodds_device_ptr",
+    "hsb_refresh_level", "hsb_last_error", "hsb_status_string", "hsb_get_launch_count", "hsb_get_gather_mode",
+    "hsb_set_tuning", "hsb_version",
+]
+
+
+class HsbConfig(C.Structure):
+    _fields_ = [
+        ("map_resolution", C.c_float),
+        ("map_size_x", C.c_int),
+        ("map_size_y", C.c_int),
+        ("start_x", C.c_float),
+        ("start_y", C.c_float),
+        ("levels", C.c_int),
+        ("device", C.c_int),
+        ("max_iterations", C.c_int * HSB_MAX_LEVELS),
+        ("update_factor_free", C.c_float),
+        ("update_factor_occupied", C.c_float),
+        ("gather_mode", C.c_int),
+        ("reserved", C.c_int * 7),
+    ]
+
+
+class HsbError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"hsb status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load lib/libhsb200.so (built in-tree by hector_slam_b200.build). Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} not found — build it with `python -m hector_slam_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, f, i, fp, ip = C.c_void_p, C.c_float, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)
+
+    def sig(name, res, *args):
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+
+    sig("hsb_create", i, C.POINTER(HsbConfig), C.POINTER(vp))
+    sig("hsb_destroy", i, vp)
+    sig("hsb_reset", i, vp)
+    sig("hsb_set_update_factor_free", i, vp, f)
+    sig("hsb_set_update_factor_occupied", i, vp, f)
+    sig("hsb_get_logodds_increments", i, vp, vp)
+    sig("hsb_get_scale_to_map", f, vp)
+    sig("hsb_get_map_levels", i, vp)
+    sig("hsb_get_level_info", i, vp, i, ip, ip, fp)
+    sig("hsb_map_coords_pose", i, vp, i, vp, vp)
+    sig("hsb_world_coords_pose", i, vp, i, vp, vp)
+    sig("hsb_match_data", i, vp, vp, vp, i, vp, vp, vp)
+    sig("hsb_match_batch", i, vp, i, vp, vp, vp, i, vp, vp)
+    sig("hsb_match_batch_device", i, vp, i, vp, vp, vp, i, i, vp, vp, vp)
+    sig("hsb_hessian_derivs", i, vp, i, vp, vp, i, vp, vp)
+    sig("hsb_update_by_scan", i, vp, vp, i, vp, vp)
+    sig("hsb_update_level_by_scan", i, vp, i, vp, i, vp, vp)
+    sig("hsb_on_map_updated", i, vp)
+    sig("hsb_upload_level", i, vp, i, vp)
+    sig("hsb_download_level", i, vp, i, vp)
+    sig("hsb_download_prob", i, vp, i, vp)
+    sig("hsb_level_logodds_device_ptr", vp, vp, i)
+    sig("hsb_refresh_level", i, vp, i, vp)
+    sig("hsb_last_error", C.c_char_p, vp)
+    sig("hsb_status_string", C.c_char_p, i)
+    sig("hsb_get_launch_count", C.c_uint64, vp)
+    sig("hsb_get_gather_mode", i, vp)
+    sig("hsb_set_tuning", i, vp, C.c_char_p, i)
+    sig("hsb_version", C.c_char_p)
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """Host pointer of a contiguous numpy array / torch CPU tensor, or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+class MapRepB200:
+    """The C-ABI handle with MapRepresentationInterface's method names
+    (slam_main/MapRepresentationInterface.h:38-62), numpy in / numpy out."""
+
+    def __init__(self, map_resolution: float, map_size_x: int, map_size_y: int | None = None, levels: int = 3,
+                 start=(0.5, 0.5), device: int = 0, max_iterations=None, update_factor_free: float = 0.0,
+                 update_factor_occupied: float = 0.0, gather_mode: int = GATHER_AUTO):
+        self.lib = load_library()
+        cfg = HsbConfig()
+        cfg.map_resolution = map_resolution
+        cfg.map_size_x = int(map_size_x)
+        cfg.map_size_y = int(map_size_x if map_size_y is None else map_size_y)
+        cfg.start_x, cfg.start_y = float(start[0]), float(start[1])
+        cfg.levels = int(levels)
+        cfg.device = int(device)
+        if max_iterations is not None:
+            for k, v in enumerate(max_iterations):
+                cfg.max_iterations[k] = int(v)
+        cfg.update_factor_free = update_factor_free
+        cfg.update_factor_occupied = update_factor_occupied
+        cfg.gather_mode = gather_mode
+        self.cfg = cfg
+        h = C.c_void_p()
+        st = self.lib.hsb_create(C.byref(cfg), C.byref(h))
+        if st != 0:
+            raise HsbError(st, (self.lib.hsb_last_error(None) or b"").decode())
+        self.h = h
+        self.levels = int(levels)
+        self.device = int(device)
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _check(self, st: int):
+        if st != 0:
+            raise HsbError(st, (self.lib.hsb_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hsb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tuning(self, **kw):
+        for k, v in kw.items():
+            self._check(self.lib.hsb_set_tuning(self.h, k.encode(), int(v)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.hsb_get_launch_count(self.h))
+
+    @property
+    def gather_mode(self) -> int:
+        return int(self.lib.hsb_get_gather_mode(self.h))
+
+    # -- MapRepresentationInterface ------------------------------------------------------------------
+    def reset(self):
+        self._check(self.lib.hsb_reset(self.h))
+
+    def getScaleToMap(self) -> float:
+        return float(self.lib.hsb_get_scale_to_map(self.h))
+
+    def getMapLevels(self) -> int:
+        return int(self.lib.hsb_get_map_levels(self.h))
+
+    def level_info(self, level: int):
+        sx, sy, cl = C.c_int(), C.c_int(), C.c_float()
+        self._check(self.lib.hsb_get_level_info(self.h, level, C.byref(sx), C.byref(sy), C.byref(cl)))
+        return sx.value, sy.value, cl.value
+
+    def setUpdateFactorFree(self, f: float):
+        self._check(self.lib.hsb_set_update_factor_free(self.h, f))
+
+    def setUpdateFactorOccupied(self, f: float):
+        self._check(self.lib.hsb_set_update_factor_occupied(self.h, f))
+
+    def logodds_increments(self):
+        out = np.zeros(2, np.float32)
+        self._check(self.lib.hsb_get_logodds_increments(self.h, out.ctypes.data))
+        return out
+
+    def map_coords_pose(self, level: int, world):
+        w, out = _f32(world, 3), np.zeros(3, np.float32)
+        self._check(self.lib.hsb_map_coords_pose(self.h, level, w.ctypes.data, out.ctypes.data))
+        return out
+
+    def world_coords_pose(self, level: int, mp):
+        m, out = _f32(mp, 3), np.zeros(3, np.float32)
+        self._check(self.lib.hsb_world_coords_pose(self.h, level, m.ctypes.data, out.ctypes.data))
+        return out
+
+    def matchData(self, begin_estimate_world, points_xy, cov_inout=None, origo=None):
+        """-> (pose (3,), cov (3,3)).  cov_inout is returned untouched for an empty scan."""
+        hint = _f32(begin_estimate_world, 3)
+        pts = _f32(points_xy).reshape(-1, 2)
+        pose = np.zeros(3, np.float32)
+        cov = np.zeros(9, np.float32) if cov_inout is None else _f32(cov_inout).reshape(9).copy()
+        og = None if origo is None else _f32(origo, 2)
+        self._check(self.lib.hsb_match_data(self.h, hint.ctypes.data, pts.ctypes.data if pts.size else None,
+                                            pts.shape[0], _ptr(og), pose.ctypes.data, cov.ctypes.data))
+        return pose, cov.reshape(3, 3)
+
+    def updateByScan(self, points_xy, robot_pose_world, origo=None):
+        pts = _f32(points_xy).reshape(-1, 2)
+        pose = _f32(robot_pose_world, 3)
+        og = None if origo is None else _f32(origo, 2)
+        self._check(self.lib.hsb_update_by_scan(self.h, pts.ctypes.data if pts.size else None, pts.shape[0], _ptr(og),
+                                                pose.ctypes.data))
+
+    def onMapUpdated(self):
+        self._check(self.lib.hsb_on_map_updated(self.h))
+
+    # -- finer seams -----------------------------------------------------------------------------
+    def update_level_by_scan(self, level: int, points_level_xy, robot_pose_world, origo_level=None):
+        pts = _f32(points_level_xy).reshape(-1, 2)
+        pose = _f32(robot_pose_world, 3)
+        og = None if origo_level is None else _f32(origo_level, 2)
+        self._check(self.lib.hsb_update_level_by_scan(self.h, level, pts.ctypes.data if pts.size else None,
+                                                      pts.shape[0], _ptr(og), pose.ctypes.data))
+
+    def hessian_derivs(self, level: int, pose_map, points_level_xy):
+        pts = _f32(points_level_xy).reshape(-1, 2)
+        pm = _f32(pose_map, 3)
+        H, d = np.zeros(9, np.float32), np.zeros(3, np.float32)
+        self._check(self.lib.hsb_hessian_derivs(self.h, level, pm.ctypes.data, pts.ctypes.data if pts.size else None,
+                                                pts.shape[0], H.ctypes.data, d.ctypes.data))
+        return H.reshape(3, 3), d
+
+    def match_batch(self, hints, points_xy, offsets=None, want_cov: bool = True, out_poses=None, out_cov=None):
+        """Host-buffer batch (numpy arrays or pinned torch CPU tensors). offsets=None -> every hint
+        uses the one scan `points_xy` (pose-hypothesis mode). -> (poses (B,3), cov (B,3,3) | None)"""
+        B = int(hints.shape[0])
+        if isinstance(hints, np.ndarray):
+            hints = _f32(hints).reshape(-1, 3)
+        if isinstance(points_xy, np.ndarray):
+            points_xy = _f32(points_xy).reshape(-1, 2)
+        n_shared = 0
+        if offsets is None:
+            n_shared = int(points_xy.shape[0])
+        elif isinstance(offsets, np.ndarray):
+            offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        if out_poses is None:
+            out_poses = np.zeros((B, 3), np.float32)
+        if want_cov and out_cov is None:
+            out_cov = np.zeros((B, 9), np.float32)
+        self._check(self.lib.hsb_match_batch(self.h, B, _ptr(hints), _ptr(points_xy), _ptr(offsets), n_shared,
+                                             _ptr(out_poses), _ptr(out_cov) if want_cov else None))
+        cov = None
+        if want_cov:
+            cov = out_cov.reshape(B, 3, 3) if isinstance(out_cov, np.ndarray) else out_cov
+        return out_poses, cov
+
+    def match_batch_device(self, B: int, d_hints: int, d_points: int, d_offsets: int | None, n_shared: int,
+                           max_points_per_scan: int, d_out_poses: int, d_out_cov: int | None, stream: int = 0):
+        """Raw device pointers (ints, e.g. tensor.data_ptr()) and a CUDA stream handle; asynchronous."""
+        self._check(self.lib.hsb_match_batch_device(self.h, int(B), d_hints, d_points, d_offsets, int(n_shared),
+                                                    int(max_points_per_scan), d_out_poses, d_out_cov, stream))
+
+    # -- planes ----------------------------------------------------------------------------------
+    def upload_level(self, level: int, logodds):
+        sx, sy, _ = self.level_info(level)
+        a = _f32(logodds).reshape(-1)
+        assert a.size == sx * sy, (a.size, sx, sy)
+        self._check(self.lib.hsb_upload_level(self.h, level, a.ctypes.data))
+
+    def download_level(self, level: int) -> np.ndarray:
+        sx, sy, _ = self.level_info(level)
+        out = np.zeros((sy, sx), np.float32)
+        self._check(self.lib.hsb_download_level(self.h, level, out.ctypes.data))
+        return out
+
+    def download_prob(self, level: int) -> np.ndarray:
+        sx, sy, _ = self.level_info(level)
+        out = np.zeros((sy, sx), np.float32)
+        self._check(self.lib.hsb_download_prob(self.h, level, out.ctypes.data))
+        return out
+
+    def level_logodds_device_ptr(self, level: int) -> int:
+        return int(self.lib.hsb_level_logodds_device_ptr(self.h, level) or 0)
+
+    def refresh_level(self, level: int, stream: int = 0):
+        self._check(self.lib.hsb_refresh_level(self.h, level, stream))

@@ -1,0 +1,784 @@
+// hsb_api.cu — implementation of the C-ABI in include/hector_slam_b200.h on top of the sm_100a
+// kernels in match_kernel.cuh / update_kernel.cuh.  No torch types, no CPU fallback: every entry
+// point that computes something launches a CUDA kernel or fails with an error code.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hsb_internal.h"
+#include "match_kernel.cuh"
+#include "update_kernel.cuh"
+
+namespace {
+
+struct Level {
+  int sx = 0, sy = 0;
+  float cell_length = 0.f, scale = 0.f;
+  float mtw[6] = {0}, wtm[6] = {0};
+  float* logodds = nullptr;
+  float* prob = nullptr;
+  uint32_t* stamp = nullptr;
+  uint32_t stamp_base = 0;
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex = 0;
+  cudaSurfaceObject_t surf = 0;
+  int evals = 0;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct hsb_handle {
+  hsb_config cfg;
+  int device = 0;
+  int sm_count = 148;
+  int levels = 0;
+  Level lv[HSB_MAX_LEVELS];
+  float log_odds_free = 0.f, log_odds_occ = 0.f;
+  int gather_mode = HSB_GATHER_LDG;
+  cudaStream_t stream = nullptr;      // main stream
+  cudaStream_t copy_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // device staging for the host-buffer entry points
+  DevBuf d_hints, d_pts, d_offsets, d_poses, d_cov, d_scratch;
+  // "containers of the last match" (MapRepMultiMap::dataContainers) and the update scan
+  DevBuf d_last_pts, d_upd_pts;
+  int last_n = 0;
+  float last_origo[2] = {0.f, 0.f};
+  // pinned host scratch
+  float* h_pin = nullptr;  // 64 floats
+  // tuning
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(hsb_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    h->err = buf;
+  }
+  return code;
+}
+
+#define HSB_CUDA(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      return fail((h), _e == cudaErrorMemoryAllocation ? HSB_ERR_OUT_OF_MEMORY : HSB_ERR_CUDA,     \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);     \
+    }                                                                                              \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int ensure(hsb_handle* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return HSB_OK;
+  if (b.p) HSB_CUDA(h, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  HSB_CUDA(h, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return HSB_OK;
+}
+
+// GridMapLogOdds.h:197-201 probToLogOdds (fp32 division, logf)
+float prob_to_log_odds(float prob) {
+  float odds = prob / (1.0f - prob);
+  return logf(odds);
+}
+
+// Affine-mode inverse of the 2x3 map_T_world — the arithmetic the reference's
+// `worldTmap = mapTworld.inverse()` performs (GridMapBase.h:279; order as oracle/hs_oracle.c
+// affine2_inverse).  Host code is compiled without FMA contraction (x86-64 baseline).
+void affine_inverse(const float a[6], float r[6]) {
+  volatile float det = a[0] * a[4] - a[3] * a[1];
+  float invdet = 1.0f / det;
+  float l00 = a[4] * invdet;
+  float l10 = -a[3] * invdet;
+  float l01 = -a[1] * invdet;
+  float l11 = a[0] * invdet;
+  r[0] = l00;
+  r[1] = l01;
+  r[3] = l10;
+  r[4] = l11;
+  volatile float p0 = (-l00) * a[2], p1 = (-l01) * a[5];
+  volatile float q0 = (-l10) * a[2], q1 = (-l11) * a[5];
+  r[2] = p0 + p1;
+  r[5] = q0 + q1;
+}
+
+void affine_apply_host(const float m[6], float vx, float vy, float* ox, float* oy) {
+  volatile float p0 = m[0] * vx, p1 = m[1] * vy, p2 = m[2] * 1.0f;
+  volatile float q0 = m[3] * vx, q1 = m[4] * vy, q2 = m[5] * 1.0f;
+  volatile float s1 = p1 + p2, t1 = q1 + q2;
+  *ox = p0 + s1;
+  *oy = q0 + t1;
+}
+
+int refresh_level(hsb_handle* h, int level, cudaStream_t st) {
+  Level& L = h->lv[level];
+  size_t n = (size_t)L.sx * L.sy;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  hsb::refresh_prob_kernel<<<blocks, 256, 0, st>>>(L.logodds, L.prob, L.surf, L.sx, L.sy);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  return HSB_OK;
+}
+
+int clear_level(hsb_handle* h, int level, cudaStream_t st) {
+  Level& L = h->lv[level];
+  size_t n = (size_t)L.sx * L.sy;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  hsb::clear_level_kernel<<<blocks, 256, 0, st>>>(L.logodds, L.prob, L.stamp, L.surf, L.sx, L.sy);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  L.stamp_base = 0;
+  return HSB_OK;
+}
+
+void fill_level_dev(const hsb_handle* h, int l, HsbLevelDev& d) {
+  const Level& L = h->lv[l];
+  d.prob = L.prob;
+  d.tex = L.tex;
+  d.sx = L.sx;
+  d.sy = L.sy;
+  d.lim_x = (float)L.sx - 2.0f;  // MapDimensionProperties.h:73
+  d.lim_y = (float)L.sy - 2.0f;
+  memcpy(d.mtw, L.mtw, sizeof(d.mtw));
+  memcpy(d.wtm, L.wtm, sizeof(d.wtm));
+  d.evals = L.evals;
+  d.pt_scale = (float)(1.0 / pow(2.0, (double)l));  // MapRepMultiMap.h:127
+}
+
+// ---- match launch -----------------------------------------------------------------------------
+template <int W, int G, int MODE>
+int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
+  size_t header = hsb::MatchSmem<W, G>::kHeaderBytes;
+  int cap = 0;
+  if (h->tune_stage_smem) {
+    cap = ((max_n + 1) + 1) & ~1;  // n + head padding, even
+    if (header + (size_t)G * cap * 8 > 200 * 1024) cap = 0;
+  }
+  P.pts_cap = cap;
+  size_t smem = header + (size_t)G * cap * 8;
+  auto kern = hsb::match_kernel<W, G, MODE>;
+  if (smem > 48 * 1024) {
+    HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  int grid = (P.B + G - 1) / G;
+  kern<<<grid, W * G * 32, smem, st>>>(P);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  return HSB_OK;
+}
+
+template <int MODE>
+int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int W, int G) {
+#define HSB_CASE(w, g) \
+  if (W == w && G == g) return launch_match_t<w, g, MODE>(h, P, max_n, st)
+  HSB_CASE(1, 1);
+  HSB_CASE(1, 2);
+  HSB_CASE(1, 4);
+  HSB_CASE(1, 8);
+  HSB_CASE(2, 1);
+  HSB_CASE(2, 2);
+  HSB_CASE(2, 4);
+  HSB_CASE(4, 1);
+  HSB_CASE(4, 2);
+  HSB_CASE(8, 1);
+  HSB_CASE(16, 1);
+  HSB_CASE(17, 1);
+  HSB_CASE(32, 1);
+#undef HSB_CASE
+  return fail(h, HSB_ERR_INVALID_ARG, "unsupported tuning warps_per_scan=%d scans_per_block=%d", W, G);
+}
+
+int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
+  int W = h->tune_warps_per_scan, G = h->tune_scans_per_block;
+  if (W <= 0) {
+    // enough warps to fill the chip: ~16 warps per SM
+    long want = ((long)h->sm_count * 16 + P.B - 1) / P.B;
+    W = 1;
+    while (W < want && W < 32) W *= 2;
+    if (W == 32 && max_n <= 17 * 64 && max_n > 1024) W = 17;  // 1081-pt scan: 2 points per lane
+  }
+  if (G <= 0) G = (W >= 4) ? 1 : 4 / W;
+  if (h->gather_mode == HSB_GATHER_TEX) return launch_match_mode<hsb::MODE_TEX>(h, P, max_n, st, W, G);
+  return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G);
+}
+
+void fill_match_params(const hsb_handle* h, HsbMatchParams& P) {
+  memset(&P, 0, sizeof(P));
+  P.levels = h->levels;
+  for (int l = 0; l < h->levels; ++l) fill_level_dev(h, l, P.lv[l]);
+}
+
+int destroy_level(hsb_handle* h, Level& L) {
+  if (L.tex) cudaDestroyTextureObject(L.tex);
+  if (L.surf) cudaDestroySurfaceObject(L.surf);
+  if (L.arr) cudaFreeArray(L.arr);
+  if (L.logodds) cudaFree(L.logodds);
+  if (L.prob) cudaFree(L.prob);
+  if (L.stamp) cudaFree(L.stamp);
+  L = Level();
+  (void)h;
+  return HSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hsb_version(void) { return "hector_slam_b200 0.1 (sm_100a)"; }
+
+const char* hsb_status_string(int status) {
+  switch (status) {
+    case HSB_OK: return "ok";
+    case HSB_ERR_INVALID_ARG: return "invalid argument";
+    case HSB_ERR_CUDA: return "CUDA error";
+    case HSB_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case HSB_ERR_NO_DEVICE: return "no CUDA device";
+    case HSB_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+  }
+}
+
+static std::string g_create_error;
+
+const char* hsb_last_error(const hsb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+uint64_t hsb_get_launch_count(const hsb_handle* h) { return h ? h->launches : 0; }
+int hsb_get_gather_mode(const hsb_handle* h) { return h ? h->gather_mode : 0; }
+
+int hsb_create(const hsb_config* cfg, hsb_handle** out) {
+  if (!cfg || !out) return HSB_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->levels < 1 || cfg->levels > HSB_MAX_LEVELS || cfg->map_size_x < 4 || cfg->map_size_y < 4 ||
+      !(cfg->map_resolution > 0.f)) {
+    g_create_error = "hsb_create: bad config (levels 1..8, sizes >= 4, resolution > 0)";
+    return HSB_ERR_INVALID_ARG;
+  }
+  if ((cfg->map_size_x >> (cfg->levels - 1)) < 4 || (cfg->map_size_y >> (cfg->levels - 1)) < 4) {
+    g_create_error = "hsb_create: coarsest level would be smaller than 4 cells";
+    return HSB_ERR_INVALID_ARG;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("hsb_create: no CUDA device (") + cudaGetErrorString(e) + ")";
+    return HSB_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "hsb_create: device ordinal out of range";
+    return HSB_ERR_INVALID_ARG;
+  }
+  hsb_handle* h = new (std::nothrow) hsb_handle();
+  if (!h) return HSB_ERR_OUT_OF_MEMORY;
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  h->levels = cfg->levels;
+  DeviceGuard guard(h->device);
+  int status = HSB_OK;
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    hsb_destroy(h);
+    return code;
+  };
+#define HSB_TRY(expr)            \
+  status = (expr);               \
+  if (status != HSB_OK) return bail(status)
+#define HSB_CUDA_C(expr)                                                                     \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      fail(h, HSB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));                 \
+      return bail(_e == cudaErrorMemoryAllocation ? HSB_ERR_OUT_OF_MEMORY : HSB_ERR_CUDA);   \
+    }                                                                                        \
+  } while (0)
+
+  cudaDeviceProp prop;
+  HSB_CUDA_C(cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  HSB_CUDA_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+  HSB_CUDA_C(cudaMallocHost(&h->h_pin, 64 * sizeof(float)));
+
+  h->gather_mode = cfg->gather_mode == HSB_GATHER_TEX ? HSB_GATHER_TEX : HSB_GATHER_LDG;
+  float ffree = cfg->update_factor_free > 0.f ? cfg->update_factor_free : 0.4f;      // GridMapLogOdds.h:117
+  float focc = cfg->update_factor_occupied > 0.f ? cfg->update_factor_occupied : 0.6f;  // :118
+  h->log_odds_free = prob_to_log_odds(ffree);
+  h->log_odds_occ = prob_to_log_odds(focc);
+
+  // MapRepMultiMap.h:48-72
+  volatile float total_x = cfg->map_resolution * (float)cfg->map_size_x;
+  volatile float mid_x = total_x * cfg->start_x;
+  volatile float total_y = cfg->map_resolution * (float)cfg->map_size_y;
+  volatile float mid_y = total_y * cfg->start_y;
+  float res = cfg->map_resolution;
+  int dx = cfg->map_size_x, dy = cfg->map_size_y;
+  for (int l = 0; l < h->levels; ++l) {
+    Level& L = h->lv[l];
+    L.sx = dx;
+    L.sy = dy;
+    L.cell_length = res;
+    L.scale = 1.0f / res;  // GridMapBase.h:270
+    // AlignedScaling2f(s,s) * Translation2f(off): GridMapBase.h:272
+    L.mtw[0] = L.scale;
+    L.mtw[1] = 0.f;
+    L.mtw[3] = 0.f;
+    L.mtw[4] = L.scale;
+    volatile float tx = L.scale * mid_x, ty = L.scale * mid_y;
+    L.mtw[2] = tx;
+    L.mtw[5] = ty;
+    affine_inverse(L.mtw, L.wtm);  // GridMapBase.h:279
+    int mi = cfg->max_iterations[l];
+    if (mi == 0) mi = (l == 0) ? 5 : 3;  // MapRepMultiMap.h:125,128
+    if (mi < 0) mi = 0;
+    L.evals = mi + 1;  // ScanMatcher.h:74 + :94
+    size_t n = (size_t)dx * dy;
+    HSB_CUDA_C(cudaMalloc(&L.logodds, n * sizeof(float)));
+    HSB_CUDA_C(cudaMalloc(&L.prob, n * sizeof(float)));
+    HSB_CUDA_C(cudaMalloc(&L.stamp, n * sizeof(uint32_t)));
+    if (h->gather_mode == HSB_GATHER_TEX) {
+      cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+      HSB_CUDA_C(cudaMallocArray(&L.arr, &desc, dx, dy, cudaArrayTextureGather | cudaArraySurfaceLoadStore));
+      cudaResourceDesc rd;
+      memset(&rd, 0, sizeof(rd));
+      rd.resType = cudaResourceTypeArray;
+      rd.res.array.array = L.arr;
+      cudaTextureDesc td;
+      memset(&td, 0, sizeof(td));
+      td.addressMode[0] = cudaAddressModeClamp;
+      td.addressMode[1] = cudaAddressModeClamp;
+      td.filterMode = cudaFilterModePoint;
+      td.readMode = cudaReadModeElementType;
+      td.normalizedCoords = 0;
+      HSB_CUDA_C(cudaCreateTextureObject(&L.tex, &rd, &td, nullptr));
+      HSB_CUDA_C(cudaCreateSurfaceObject(&L.surf, &rd));
+    }
+    HSB_TRY(clear_level(h, l, h->stream));
+    dx /= 2;      // MapRepMultiMap.h:67
+    dy /= 2;
+    res *= 2.0f;  // :68
+  }
+  HSB_CUDA_C(cudaStreamSynchronize(h->stream));
+#undef HSB_TRY
+#undef HSB_CUDA_C
+  *out = h;
+  return HSB_OK;
+}
+
+int hsb_destroy(hsb_handle* h) {
+  if (!h) return HSB_OK;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  for (int l = 0; l < HSB_MAX_LEVELS; ++l) destroy_level(h, h->lv[l]);
+  DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_last_pts, &h->d_upd_pts};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->copy_stream[i]) cudaStreamDestroy(h->copy_stream[i]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return HSB_OK;
+}
+
+int hsb_reset(hsb_handle* h) {
+  if (!h) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  for (int l = 0; l < h->levels; ++l) {
+    int s = clear_level(h, l, h->stream);
+    if (s != HSB_OK) return s;
+  }
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HSB_OK;
+}
+
+int hsb_set_update_factor_free(hsb_handle* h, float factor) {
+  if (!h) return HSB_ERR_INVALID_ARG;
+  h->log_odds_free = prob_to_log_odds(factor);
+  return HSB_OK;
+}
+int hsb_set_update_factor_occupied(hsb_handle* h, float factor) {
+  if (!h) return HSB_ERR_INVALID_ARG;
+  h->log_odds_occ = prob_to_log_odds(factor);
+  return HSB_OK;
+}
+int hsb_get_logodds_increments(hsb_handle* h, float out[2]) {
+  if (!h || !out) return HSB_ERR_INVALID_ARG;
+  out[0] = h->log_odds_free;
+  out[1] = h->log_odds_occ;
+  return HSB_OK;
+}
+
+int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
+  if (!h || !key) return HSB_ERR_INVALID_ARG;
+  if (!strcmp(key, "warps_per_scan")) h->tune_warps_per_scan = value;
+  else if (!strcmp(key, "scans_per_block")) h->tune_scans_per_block = value;
+  else if (!strcmp(key, "stage_smem")) h->tune_stage_smem = value;
+  else if (!strcmp(key, "chunk")) h->tune_chunk = value;
+  else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
+  return HSB_OK;
+}
+
+float hsb_get_scale_to_map(const hsb_handle* h) { return h ? h->lv[0].scale : 0.f; }
+int hsb_get_map_levels(const hsb_handle* h) { return h ? h->levels : 0; }
+
+int hsb_get_level_info(const hsb_handle* h, int level, int* size_x, int* size_y, float* cell_length) {
+  if (!h || level < 0 || level >= h->levels) return HSB_ERR_INVALID_ARG;
+  if (size_x) *size_x = h->lv[level].sx;
+  if (size_y) *size_y = h->lv[level].sy;
+  if (cell_length) *cell_length = h->lv[level].cell_length;
+  return HSB_OK;
+}
+
+int hsb_map_coords_pose(const hsb_handle* h, int level, const float world[3], float out[3]) {
+  if (!h || level < 0 || level >= h->levels || !world || !out) return HSB_ERR_INVALID_ARG;
+  affine_apply_host(h->lv[level].mtw, world[0], world[1], &out[0], &out[1]);
+  out[2] = world[2];
+  return HSB_OK;
+}
+int hsb_world_coords_pose(const hsb_handle* h, int level, const float map[3], float out[3]) {
+  if (!h || level < 0 || level >= h->levels || !map || !out) return HSB_ERR_INVALID_ARG;
+  affine_apply_host(h->lv[level].wtm, map[0], map[1], &out[0], &out[1]);
+  out[2] = map[2];
+  return HSB_OK;
+}
+
+// ---- matching ----------------------------------------------------------------------------------
+
+int hsb_match_batch_device(hsb_handle* h, int B, const float* d_hints, const float* d_pts, const int* d_offsets,
+                           int n_shared, int max_points_per_scan, float* d_out_poses, float* d_out_cov, void* stream) {
+  if (!h || B < 0 || !d_hints || !d_out_poses) return HSB_ERR_INVALID_ARG;
+  if (B == 0) return HSB_OK;
+  if (!d_offsets && n_shared < 0) return fail(h, HSB_ERR_INVALID_ARG, "shared-scan mode needs n_shared >= 0");
+  if (!d_pts && (d_offsets || n_shared > 0)) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  DeviceGuard guard(h->device);
+  HsbMatchParams P;
+  fill_match_params(h, P);
+  P.B = B;
+  P.hints = d_hints;
+  P.pts = reinterpret_cast<const float2*>(d_pts);
+  P.offsets = d_offsets;
+  P.n_shared = d_offsets ? 0 : n_shared;
+  P.out_poses = d_out_poses;
+  P.out_cov = d_out_cov;
+  int max_n = d_offsets ? max_points_per_scan : n_shared;
+  if (max_n < 0) max_n = 0;
+  return launch_match(h, P, max_n, (cudaStream_t)stream);
+}
+
+int hsb_match_data(hsb_handle* h, const float hint[3], const float* pts, int n, const float origo[2], float out_pose[3],
+                   float cov_inout[9]) {
+  if (!h || !hint || !out_pose || n < 0 || (n > 0 && !pts)) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  // MapRepMultiMap::matchData fills dataContainers[] from this scan (MapRepMultiMap.h:127) whenever
+  // there is a coarse level; hsb_update_by_scan reuses it for the coarse levels (:143).
+  int s = ensure(h, h->d_last_pts, (size_t)(n > 0 ? n : 1) * 8 + 16);
+  if (s != HSB_OK) return s;
+  s = ensure(h, h->d_scratch, 64 * sizeof(float));
+  if (s != HSB_OK) return s;
+  float* d_s = static_cast<float*>(h->d_scratch.p);  // [0..2] hint, [4..6] pose, [8..16] cov
+  cudaStream_t st = h->stream;
+  if (n > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_last_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  h->last_n = n;
+  h->last_origo[0] = origo ? origo[0] : 0.f;
+  h->last_origo[1] = origo ? origo[1] : 0.f;
+  memcpy(h->h_pin, hint, 3 * sizeof(float));
+  HSB_CUDA(h, cudaMemcpyAsync(d_s, h->h_pin, 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  s = hsb_match_batch_device(h, 1, d_s, static_cast<const float*>(h->d_last_pts.p), nullptr, n, n, d_s + 4, d_s + 8, st);
+  if (s != HSB_OK) return s;
+  HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 4, d_s + 4, 13 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  memcpy(out_pose, h->h_pin + 4, 3 * sizeof(float));
+  if (cov_inout && n > 0) memcpy(cov_inout, h->h_pin + 8, 9 * sizeof(float));
+  return HSB_OK;
+}
+
+int hsb_match_batch(hsb_handle* h, int B, const float* hints, const float* pts, const int* offsets, int n_shared,
+                    float* out_poses, float* out_cov) {
+  if (!h || B < 0 || !hints || !out_poses) return HSB_ERR_INVALID_ARG;
+  if (B == 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  size_t total = offsets ? (size_t)offsets[B] : (size_t)(n_shared > 0 ? n_shared : 0);
+  if (total > 0 && !pts) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  int s;
+  if ((s = ensure(h, h->d_hints, (size_t)B * 12)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_pts, total * 8 + 16)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_offsets, (size_t)(B + 1) * 4)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_poses, (size_t)B * 12)) != HSB_OK) return s;
+  if (out_cov && (s = ensure(h, h->d_cov, (size_t)B * 36)) != HSB_OK) return s;
+  float* d_hints = static_cast<float*>(h->d_hints.p);
+  float* d_pts = static_cast<float*>(h->d_pts.p);
+  int* d_off = static_cast<int*>(h->d_offsets.p);
+  float* d_poses = static_cast<float*>(h->d_poses.p);
+  float* d_cov = out_cov ? static_cast<float*>(h->d_cov.p) : nullptr;
+
+  int max_n = 0;
+  if (offsets) {
+    for (int b = 0; b < B; ++b) {
+      int n = offsets[b + 1] - offsets[b];
+      if (n < 0) return fail(h, HSB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+      if (n > max_n) max_n = n;
+    }
+  } else {
+    max_n = n_shared > 0 ? n_shared : 0;
+  }
+
+  // Pipeline: the batch is cut into chunks; chunk c's host->device copy runs on copy stream c%2
+  // while chunk c-1 is being matched, and results stream back behind each kernel.
+  int chunk = h->tune_chunk > 0 ? h->tune_chunk : (B >= 2048 ? (B + 3) / 4 : B);
+  if (!offsets) chunk = B;  // shared scan: nothing big to overlap
+  cudaStream_t s0 = h->copy_stream[0];
+  if (offsets) {
+    HSB_CUDA(h, cudaMemcpyAsync(d_off, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s0));
+  } else if (total > 0) {
+    HSB_CUDA(h, cudaMemcpyAsync(d_pts, pts, total * 8, cudaMemcpyHostToDevice, s0));
+  }
+  HSB_CUDA(h, cudaMemcpyAsync(d_hints, hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
+  HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
+  HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
+  int ci = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
+    int b1 = b0 + chunk < B ? b0 + chunk : B;
+    cudaStream_t st = h->copy_stream[ci & 1];
+    if (offsets) {
+      size_t p0 = (size_t)offsets[b0], p1 = (size_t)offsets[b1];
+      if (p1 > p0) HSB_CUDA(h, cudaMemcpyAsync(d_pts + 2 * p0, pts + 2 * p0, (p1 - p0) * 8, cudaMemcpyHostToDevice, st));
+    }
+    s = hsb_match_batch_device(h, b1 - b0, d_hints + 3 * (size_t)b0, d_pts, offsets ? d_off + b0 : nullptr, n_shared, max_n,
+                               d_poses + 3 * (size_t)b0, d_cov ? d_cov + 9 * (size_t)b0 : nullptr, st);
+    if (s != HSB_OK) return s;
+    HSB_CUDA(h, cudaMemcpyAsync(out_poses + 3 * (size_t)b0, d_poses + 3 * (size_t)b0, (size_t)(b1 - b0) * 12,
+                                cudaMemcpyDeviceToHost, st));
+    if (out_cov)
+      HSB_CUDA(h, cudaMemcpyAsync(out_cov + 9 * (size_t)b0, d_cov + 9 * (size_t)b0, (size_t)(b1 - b0) * 36,
+                                  cudaMemcpyDeviceToHost, st));
+  }
+  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[0]));
+  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[1]));
+  return HSB_OK;
+}
+
+int hsb_hessian_derivs(hsb_handle* h, int level, const float pose_map[3], const float* pts, int n, float H_out[9],
+                       float dTr_out[3]) {
+  if (!h || level < 0 || level >= h->levels || !pose_map || n < 0 || (n > 0 && !pts) || !H_out || !dTr_out)
+    return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int s;
+  if ((s = ensure(h, h->d_pts, (size_t)(n > 0 ? n : 1) * 8 + 16)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_scratch, 64 * sizeof(float))) != HSB_OK) return s;
+  cudaStream_t st = h->stream;
+  if (n > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  HsbLevelDev L;
+  fill_level_dev(h, level, L);
+  float* d_out = static_cast<float*>(h->d_scratch.p) + 32;
+  if (h->gather_mode == HSB_GATHER_TEX)
+    hsb::hessian_kernel<hsb::MODE_TEX><<<1, 256, 0, st>>>(L, static_cast<const float2*>(h->d_pts.p), n, pose_map[0],
+                                                          pose_map[1], pose_map[2], d_out);
+  else
+    hsb::hessian_kernel<hsb::MODE_LDG><<<1, 256, 0, st>>>(L, static_cast<const float2*>(h->d_pts.p), n, pose_map[0],
+                                                          pose_map[1], pose_map[2], d_out);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 32, d_out, 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  memcpy(H_out, h->h_pin + 32, 9 * sizeof(float));
+  memcpy(dTr_out, h->h_pin + 41, 3 * sizeof(float));
+  return HSB_OK;
+}
+
+// ---- map writing -------------------------------------------------------------------------------
+
+static int run_update(hsb_handle* h, HsbUpdateParams& P, int max_n) {
+  if (max_n <= 0) return HSB_OK;
+  cudaStream_t st = h->stream;
+  int blocks = (max_n + 7) / 8;
+  int cap = h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  dim3 grid(blocks, P.levels);
+  hsb::update_kernel<false><<<grid, 256, 0, st>>>(P);
+  hsb::update_kernel<true><<<grid, 256, 0, st>>>(P);
+  h->launches += 2;
+  HSB_CUDA(h, cudaGetLastError());
+  return HSB_OK;
+}
+
+static int next_stamp_base(hsb_handle* h, int level, uint32_t* base) {
+  Level& L = h->lv[level];
+  if (L.stamp_base > 0xfffffff0u - 8u) {  // wrap guard: forget old stamps
+    HSB_CUDA(h, cudaMemsetAsync(L.stamp, 0, (size_t)L.sx * L.sy * sizeof(uint32_t), h->stream));
+    L.stamp_base = 0;
+  }
+  *base = L.stamp_base;
+  L.stamp_base += 4;
+  return HSB_OK;
+}
+
+static void fill_update_level(hsb_handle* h, int l, HsbUpdateLevelDev& d) {
+  const Level& L = h->lv[l];
+  memset(&d, 0, sizeof(d));
+  d.logodds = L.logodds;
+  d.prob = L.prob;
+  d.stamp = L.stamp;
+  d.surf = L.surf;
+  d.sx = L.sx;
+  d.sy = L.sy;
+  memcpy(d.mtw, L.mtw, sizeof(d.mtw));
+}
+
+int hsb_update_by_scan(hsb_handle* h, const float* pts, int n, const float origo[2], const float pose[3]) {
+  if (!h || !pose || n < 0 || (n > 0 && !pts)) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int s;
+  if ((s = ensure(h, h->d_upd_pts, (size_t)(n > 0 ? n : 1) * 8 + 16)) != HSB_OK) return s;
+  cudaStream_t st = h->stream;
+  if (n > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_upd_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  HsbUpdateParams P;
+  memset(&P, 0, sizeof(P));
+  P.levels = h->levels;
+  memcpy(P.pose_world, pose, 3 * sizeof(float));
+  P.log_odds_free = h->log_odds_free;
+  P.log_odds_occ = h->log_odds_occ;
+  int max_n = 0;
+  for (int l = 0; l < h->levels; ++l) {
+    HsbUpdateLevelDev& d = P.lv[l];
+    fill_update_level(h, l, d);
+    d.pt_scale = (float)(1.0 / pow(2.0, (double)l));
+    if (l == 0) {  // MapRepMultiMap.h:140-141
+      d.pts = static_cast<const float2*>(h->d_upd_pts.p);
+      d.n = n;
+      d.origo_x = origo ? origo[0] : 0.f;
+      d.origo_y = origo ? origo[1] : 0.f;
+    } else {  // :143 — the container left behind by the last matchData
+      d.pts = static_cast<const float2*>(h->d_last_pts.p);
+      d.n = h->last_n;
+      d.origo_x = h->last_origo[0];
+      d.origo_y = h->last_origo[1];
+    }
+    // an empty container still advances the stamps in the reference (OccGridMapBase.h:164-167); no-op here
+    d.active = d.n > 0;
+    if (d.active) {
+      if ((s = next_stamp_base(h, l, &d.stamp_base)) != HSB_OK) return s;
+      if (d.n > max_n) max_n = d.n;
+    }
+  }
+  if ((s = run_update(h, P, max_n)) != HSB_OK) return s;
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  return HSB_OK;
+}
+
+int hsb_update_level_by_scan(hsb_handle* h, int level, const float* pts, int n, const float origo[2], const float pose[3]) {
+  if (!h || level < 0 || level >= h->levels || !pose || n < 0 || (n > 0 && !pts)) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int s;
+  if ((s = ensure(h, h->d_upd_pts, (size_t)(n > 0 ? n : 1) * 8 + 16)) != HSB_OK) return s;
+  cudaStream_t st = h->stream;
+  if (n > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_upd_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  HsbUpdateParams P;
+  memset(&P, 0, sizeof(P));
+  P.levels = 1;
+  memcpy(P.pose_world, pose, 3 * sizeof(float));
+  P.log_odds_free = h->log_odds_free;
+  P.log_odds_occ = h->log_odds_occ;
+  HsbUpdateLevelDev& d = P.lv[0];
+  fill_update_level(h, level, d);
+  d.pt_scale = 1.0f;
+  d.pts = static_cast<const float2*>(h->d_upd_pts.p);
+  d.n = n;
+  d.origo_x = origo ? origo[0] : 0.f;
+  d.origo_y = origo ? origo[1] : 0.f;
+  d.active = n > 0;
+  if (d.active && (s = next_stamp_base(h, level, &d.stamp_base)) != HSB_OK) return s;
+  if ((s = run_update(h, P, n)) != HSB_OK) return s;
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  return HSB_OK;
+}
+
+int hsb_on_map_updated(hsb_handle* h) {
+  if (!h) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HSB_OK;
+}
+
+// ---- planes ------------------------------------------------------------------------------------
+
+int hsb_upload_level(hsb_handle* h, int level, const float* logodds_host) {
+  if (!h || level < 0 || level >= h->levels || !logodds_host) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  HSB_CUDA(h, cudaMemcpyAsync(L.logodds, logodds_host, (size_t)L.sx * L.sy * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  int s = refresh_level(h, level, h->stream);
+  if (s != HSB_OK) return s;
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HSB_OK;
+}
+
+int hsb_download_level(hsb_handle* h, int level, float* out) {
+  if (!h || level < 0 || level >= h->levels || !out) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  HSB_CUDA(h, cudaMemcpyAsync(out, L.logodds, (size_t)L.sx * L.sy * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HSB_OK;
+}
+
+int hsb_download_prob(hsb_handle* h, int level, float* out) {
+  if (!h || level < 0 || level >= h->levels || !out) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  if (L.arr) {  // read what the texture path sees
+    HSB_CUDA(h, cudaMemcpy2DFromArrayAsync(out, (size_t)L.sx * sizeof(float), L.arr, 0, 0, (size_t)L.sx * sizeof(float), L.sy,
+                                           cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    HSB_CUDA(h, cudaMemcpyAsync(out, L.prob, (size_t)L.sx * L.sy * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HSB_OK;
+}
+
+void* hsb_level_logodds_device_ptr(hsb_handle* h, int level) {
+  if (!h || level < 0 || level >= h->levels) return nullptr;
+  return h->lv[level].logodds;
+}
+
+int hsb_refresh_level(hsb_handle* h, int level, void* stream) {
+  if (!h || level < 0 || level >= h->levels) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  return refresh_level(h, level, (cudaStream_t)stream);
+}
+
+}  // extern "C"

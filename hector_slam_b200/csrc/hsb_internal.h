@@ -1,0 +1,59 @@
+// hsb_internal.h — shared host/device declarations of the B200 scan matcher (not installed).
+#ifndef HSB_INTERNAL_H
+#define HSB_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hector_slam_b200.h"
+
+// Per-level constants the kernels need.  The two affine maps are kept as the full 2x3 matrices
+// the reference builds (GridMapBase.h:265-280) so that device code can evaluate them term by
+// term in the same order as the oracle (oracle/hs_oracle.c affine2_apply).
+struct HsbLevelDev {
+  const float* prob;         // probability plane, row-major [sy][sx]
+  cudaTextureObject_t tex;   // same plane as a gather-capable 2-D texture (0 if unused)
+  int sx, sy;
+  float lim_x, lim_y;        // size - 2 (MapDimensionProperties.h:73)
+  float mtw[6];              // map_T_world  m[2][3] row-major
+  float wtm[6];              // world_T_map  m[2][3] row-major
+  int evals;                 // maxIterations + 1 (ScanMatcher.h:74,94)
+  float pt_scale;            // 2^-level (MapRepMultiMap.h:127)
+};
+
+struct HsbMatchParams {
+  HsbLevelDev lv[HSB_MAX_LEVELS];
+  int levels;
+  int B;
+  const float* hints;   // B x 3
+  const float2* pts;    // all scans, interleaved xy
+  const int* offsets;   // B + 1, or nullptr in shared-scan mode
+  int n_shared;
+  float* out_poses;     // B x 3
+  float* out_cov;       // B x 9 or nullptr
+  int pts_cap;          // points of smem staging per scan group (0 = read points from global)
+};
+
+struct HsbUpdateLevelDev {
+  float* logodds;
+  float* prob;
+  uint32_t* stamp;
+  cudaSurfaceObject_t surf;  // 0 if the level has no CUDA-array twin
+  int sx, sy;
+  float mtw[6];
+  float pt_scale;            // applied to points and origo (2^-level), 1 for per-level calls
+  const float2* pts;         // scan used for this level
+  int n;
+  float origo_x, origo_y;    // already in the units of `pts` before pt_scale
+  uint32_t stamp_base;       // this scan's stamps: base+1 free, base+2 occupied, base+3 applied
+  int active;
+};
+
+struct HsbUpdateParams {
+  HsbUpdateLevelDev lv[HSB_MAX_LEVELS];
+  int levels;
+  float pose_world[3];
+  float log_odds_free, log_odds_occ;
+};
+
+#endif

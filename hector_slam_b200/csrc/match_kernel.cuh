@@ -1,0 +1,356 @@
+// match_kernel.cuh — K1: whole multi-level Gauss-Newton scan match on the device (sm_100a).
+//
+// What it replaces (paths under /root/reference/hector_mapping/include/hector_slam_lib/):
+//   MapRepMultiMap::matchData                 slam_main/MapRepMultiMap.h:116-132  (level schedule)
+//   ScanMatcher::matchData                    matcher/ScanMatcher.h:54-190         (GN outer loop)
+//   ScanMatcher::estimateTransformationLogLh  matcher/ScanMatcher.h:194-221        (gate, 3x3 solve, clamp)
+//   OccGridMapUtil::getCompleteHessianDerivs  map/OccGridMapUtil.h:64-104          (H / dTr accumulation)
+//   OccGridMapUtil::interpMapValueWithDerivatives  map/OccGridMapUtil.h:287-347    (bilinear value + gradient)
+//
+// Shape: a "group" of W warps owns one scan; G groups share a CTA; the grid is persistent and
+// strides over the batch.  The scan's endpoints are staged once into shared memory with one TMA
+// bulk copy (cp.async.bulk + mbarrier); every Gauss-Newton evaluation then walks the endpoints
+// lane-strided, gathers the four probability cells per endpoint (four LDGs on the linear plane or
+// one tex2Dgather on the block-linear twin), accumulates the 6+3 sums in registers, reduces them
+// with warp shuffles (+ one shared-memory exchange when W > 1) and every thread of the group
+// redundantly solves the 3x3 system, so the pose never leaves registers between evaluations and
+// levels.  No host round trip, no global-memory traffic besides the gathers and 48 B of result.
+#ifndef HSB_MATCH_KERNEL_CUH
+#define HSB_MATCH_KERNEL_CUH
+
+#include "hsb_internal.h"
+
+namespace hsb {
+
+enum { MODE_LDG = 1, MODE_TEX = 2 };
+
+struct Acc {
+  float h00, h11, h22, h01, h02, h12, d0, d1, d2;
+};
+
+__device__ __forceinline__ void acc_zero(Acc& a) { a.h00 = a.h11 = a.h22 = a.h01 = a.h02 = a.h12 = a.d0 = a.d1 = a.d2 = 0.f; }
+
+// out[r] = m[r][0]*vx + (m[r][1]*vy + m[r][2]*1), each operation rounded separately — the order
+// the oracle fixes for Transform * vector (oracle/shim/Eigen/Geometry).  Used for the
+// world<->map pose conversions (GridMapBase.h:226-239), where we want the oracle's bits.
+__device__ __forceinline__ void affine_apply_exact(const float* m, float vx, float vy, float& ox, float& oy) {
+  ox = __fadd_rn(__fmul_rn(m[0], vx), __fadd_rn(__fmul_rn(m[1], vy), m[2]));
+  oy = __fadd_rn(__fmul_rn(m[3], vx), __fadd_rn(__fmul_rn(m[4], vy), m[5]));
+}
+
+// util::normalize_angle, UtilFunctions.h:37-49 (double arithmetic because M_PI is a double).
+__device__ __forceinline__ float normalize_angle(float angle) {
+  const double two_pi = 2.0 * 3.14159265358979323846;
+  float a = (float)fmod(fmod((double)angle, two_pi) + two_pi, two_pi);
+  if ((double)a > 3.14159265358979323846) a = (float)((double)a - two_pi);
+  return a;
+}
+
+// Eigen's fixed-size 3x3 inverse times vector (ScanMatcher.h:205 `H.inverse() * dTr`): cyclic
+// cofactors, det from column 0, multiply by 1/det, no pivoting — restated with explicitly rounded
+// operations (no FMA contraction) because H is often ill-conditioned and the cancellation in the
+// cofactors is where a different rounding would be amplified.  Same order as
+// oracle/hs_oracle.c inverse3_times.
+__device__ __forceinline__ float cof(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+
+__device__ __forceinline__ void solve3(const Acc& s, float& o0, float& o1, float& o2) {
+  // m = [[h00,h01,h02],[h01,h11,h12],[h02,h12,h22]]
+  const float m00 = s.h00, m01 = s.h01, m02 = s.h02, m10 = s.h01, m11 = s.h11, m12 = s.h12, m20 = s.h02, m21 = s.h12,
+              m22 = s.h22;
+  // cof(i,j) = m[i1][j1]*m[i2][j2] - m[i1][j2]*m[i2][j1], i1=(i+1)%3 ...
+  const float c00 = cof(m11, m22, m12, m21);
+  const float c10 = cof(m21, m02, m22, m01);
+  const float c20 = cof(m01, m12, m02, m11);
+  const float det = __fadd_rn(__fmul_rn(c00, m00), __fadd_rn(__fmul_rn(c10, m10), __fmul_rn(c20, m20)));
+  const float invdet = __fdiv_rn(1.0f, det);
+  const float c01 = cof(m12, m20, m10, m22);
+  const float c11 = cof(m22, m00, m20, m02);
+  const float c21 = cof(m02, m10, m00, m12);
+  const float c02 = cof(m10, m21, m11, m20);
+  const float c12 = cof(m20, m01, m21, m00);
+  const float c22 = cof(m00, m11, m01, m10);
+  // inv(i,j) = cof(j,i) * invdet
+  const float i00 = __fmul_rn(c00, invdet), i01 = __fmul_rn(c10, invdet), i02 = __fmul_rn(c20, invdet);
+  const float i10 = __fmul_rn(c01, invdet), i11 = __fmul_rn(c11, invdet), i12 = __fmul_rn(c21, invdet);
+  const float i20 = __fmul_rn(c02, invdet), i21 = __fmul_rn(c12, invdet), i22 = __fmul_rn(c22, invdet);
+  o0 = __fadd_rn(__fmul_rn(i00, s.d0), __fadd_rn(__fmul_rn(i01, s.d1), __fmul_rn(i02, s.d2)));
+  o1 = __fadd_rn(__fmul_rn(i10, s.d0), __fadd_rn(__fmul_rn(i11, s.d1), __fmul_rn(i12, s.d2)));
+  o2 = __fadd_rn(__fmul_rn(i20, s.d0), __fadd_rn(__fmul_rn(i21, s.d1), __fmul_rn(i22, s.d2)));
+}
+
+// One endpoint of one evaluation: OccGridMapUtil.h:76-98 with :287-347 inlined.
+//   cs, ss : cos/sin of the pose angle, pre-multiplied by the level's point scale 2^-k (exact,
+//            so (cs*px) equals the reference's c * (px * 2^-k) bit for bit)
+//   x, y   : pose translation in level cells
+template <int MODE>
+__device__ __forceinline__ void eval_point(const HsbLevelDev& L, float px, float py, float cs, float ss, float x, float y,
+                                           Acc& a) {
+  // T * p with T = Translation(x,y) * Rotation(psi) (OccGridMapUtil.h:80,349-352)
+  const float rx = cs * px - ss * py;  // rotated endpoint (also d(q)/d(psi) terms below)
+  const float ry = ss * px + cs * py;
+  const float qx = rx + x;
+  const float qy = ry + y;
+  // pointOutOfMapBounds, MapDimensionProperties.h:65-68; written so that NaN is OUT (the
+  // reference lets NaN through and then indexes with it — SURVEY.md Q4)
+  const bool inside = (qx >= 0.0f) && (qx <= L.lim_x) && (qy >= 0.0f) && (qy <= L.lim_y);
+  if (!inside) return;  // value 0, gradient 0: contributes nothing (OccGridMapUtil.h:290-292)
+  const int ix = (int)qx, iy = (int)qy;                   // :295
+  const float fx = qx - (float)ix, fy = qy - (float)iy;   // :298
+  float i0, i1, i2, i3;
+  if (MODE == MODE_TEX) {
+    // point-sampled 2x2 footprint: texel centres (ix, iy)..(ix+1, iy+1); coordinates are exact
+    // half-integers + 0.5 so the unit's fixed-point conversion cannot pick a neighbour
+    const float4 g = tex2Dgather<float4>(L.tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
+    i0 = g.w;  // (ix  , iy  )
+    i1 = g.z;  // (ix+1, iy  )
+    i2 = g.x;  // (ix  , iy+1)
+    i3 = g.y;  // (ix+1, iy+1)
+  } else {
+    const float* p = L.prob + (size_t)iy * (size_t)L.sx + (size_t)ix;  // :302
+    i0 = __ldg(p);
+    i1 = __ldg(p + 1);
+    i2 = __ldg(p + L.sx);
+    i3 = __ldg(p + L.sx + 1);
+  }
+  const float xi = 1.0f - fx, yi = 1.0f - fy;
+  const float m = (i0 * xi + i1 * fx) * yi + (i2 * xi + i3 * fx) * fy;  // :342-343
+  const float gx = -((i0 - i1) * xi + (i2 - i3) * fx);                  // :344 (x-weights, as the reference)
+  const float gy = -((i0 - i2) * yi + (i1 - i3) * fy);                  // :345
+  const float f = 1.0f - m;                                             // :82
+  // rotDeriv = (-sin*px - cos*py)*gx + (cos*px - sin*py)*gy = (-ry)*gx + rx*gy     :87
+  const float r = rx * gy - ry * gx;
+  a.d0 += gx * f;
+  a.d1 += gy * f;
+  a.d2 += r * f;
+  a.h00 += gx * gx;
+  a.h11 += gy * gy;
+  a.h22 += r * r;
+  a.h01 += gx * gy;
+  a.h02 += gx * r;
+  a.h12 += gy * r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void warp_reduce(Acc& a) {
+  a.h00 = warp_sum(a.h00);
+  a.h11 = warp_sum(a.h11);
+  a.h22 = warp_sum(a.h22);
+  a.h01 = warp_sum(a.h01);
+  a.h02 = warp_sum(a.h02);
+  a.h12 = warp_sum(a.h12);
+  a.d0 = warp_sum(a.d0);
+  a.d1 = warp_sum(a.d1);
+  a.d2 = warp_sum(a.d2);
+}
+
+// ---- mbarrier / bulk-copy helpers (TMA 1-D path) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Shared-memory carve-up for G groups: [G] mbarriers | [G][2][W][12] reduction slots | points
+template <int W, int G>
+struct MatchSmem {
+  static constexpr int kRedFloats = (W > 1) ? G * 2 * W * 12 : 0;
+  static constexpr int kHeaderBytes = ((G * 8 + kRedFloats * 4) + 15) / 16 * 16;
+};
+
+template <int W, int G, int MODE>
+__global__ void __launch_bounds__(W * G * 32)
+    match_kernel(const __grid_constant__ HsbMatchParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* red_all = reinterpret_cast<float*>(smem_raw + G * 8);
+  float2* spts_all = reinterpret_cast<float2*>(smem_raw + MatchSmem<W, G>::kHeaderBytes);
+
+  constexpr int GT = W * 32;  // threads per group
+  const int g = threadIdx.x / GT;
+  const int t = threadIdx.x - g * GT;
+  const int w = t >> 5;
+  const int lane = t & 31;
+  const int cap = P.pts_cap;
+  float2* spts = spts_all + (size_t)g * cap;
+  float* red = red_all + g * (2 * W * 12);
+  uint64_t* mbar = mbars + g;
+
+  if (t == 0) mbar_init(mbar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  uint32_t phase = 0;
+  int red_flip = 0;
+  for (int scan = blockIdx.x * G + g; scan < P.B; scan += gridDim.x * G) {
+    int beg, n;
+    if (P.offsets) {
+      beg = P.offsets[scan];
+      n = P.offsets[scan + 1] - beg;
+    } else {
+      beg = 0;
+      n = P.n_shared;
+    }
+    const float2* gpts = P.pts + beg;
+    const float2* pts = gpts;
+    if (cap > 0 && n < cap && n > 0) {
+      // Stage the scan into shared memory.  Point i goes to spts[i + head] where head = 1 iff the
+      // scan starts on an odd point (8- but not 16-byte aligned), so that global and shared
+      // addresses share their 16-byte phase and the even-aligned body can move as ONE bulk copy;
+      // a misaligned first point / odd last point is carried by plain stores.
+      const int head = (int)(((uintptr_t)gpts >> 3) & 1);
+      const int body = (n - head) & ~1;
+      float2* sdst = spts + head;
+      if (t == 0) {
+        if (body > 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(mbar, (uint32_t)body * 8u);
+          bulk_g2s(sdst + head, gpts + head, (uint32_t)body * 8u, mbar);
+        }
+        if (head) sdst[0] = gpts[0];
+        if (head + body < n) sdst[n - 1] = gpts[n - 1];
+      }
+      if (body > 0) {
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+      }
+      group_sync(1 + g, GT);  // head/tail stores visible to the whole group
+      pts = sdst;
+    }
+
+    float wx = P.hints[3 * scan + 0], wy = P.hints[3 * scan + 1], wpsi = P.hints[3 * scan + 2];
+    Acc last;
+    acc_zero(last);
+    if (n > 0) {
+      for (int lvl = P.levels - 1; lvl >= 0; --lvl) {
+        const HsbLevelDev& L = P.lv[lvl];
+        float ex, ey, epsi = wpsi;
+        affine_apply_exact(L.mtw, wx, wy, ex, ey);  // ScanMatcher.h:70 getMapCoordsPose
+        for (int e = 0; e < L.evals; ++e) {          // ScanMatcher.h:74 + :94-97
+          double sd, cd;
+          sincos((double)epsi, &sd, &cd);            // OccGridMapUtil.h:70-71 (sinf/cosf, correctly rounded)
+          const float cs = (float)cd * L.pt_scale, ss = (float)sd * L.pt_scale;
+          Acc a;
+          acc_zero(a);
+#pragma unroll 4
+          for (int i = t; i < n; i += GT) {
+            const float2 p = pts[i];
+            eval_point<MODE>(L, p.x, p.y, cs, ss, ex, ey, a);
+          }
+          warp_reduce(a);
+          if (W > 1) {
+            float* slot = red + (red_flip * W + w) * 12;
+            if (lane == 0) {
+              slot[0] = a.h00; slot[1] = a.h11; slot[2] = a.h22; slot[3] = a.h01; slot[4] = a.h02;
+              slot[5] = a.h12; slot[6] = a.d0;  slot[7] = a.d1;  slot[8] = a.d2;
+            }
+            group_sync(1 + g, GT);
+            const float* base = red + red_flip * W * 12;
+            acc_zero(a);
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+              const float* s = base + k * 12;
+              a.h00 += s[0]; a.h11 += s[1]; a.h22 += s[2]; a.h01 += s[3]; a.h02 += s[4];
+              a.h12 += s[5]; a.d0 += s[6];  a.d1 += s[7];  a.d2 += s[8];
+            }
+            red_flip ^= 1;
+          }
+          last = a;
+          if (a.h00 != 0.0f && a.h11 != 0.0f) {  // ScanMatcher.h:201
+            float d0, d1, d2;
+            solve3(a, d0, d1, d2);               // :205
+            if (d2 > 0.2f) d2 = 0.2f;            // :209-215
+            else if (d2 < -0.2f) d2 = -0.2f;
+            ex = __fadd_rn(ex, d0);              // :217
+            ey = __fadd_rn(ey, d1);
+            epsi = __fadd_rn(epsi, d2);
+          }
+        }
+        epsi = normalize_angle(epsi);                 // ScanMatcher.h:170
+        affine_apply_exact(L.wtm, ex, ey, wx, wy);    // :186 getWorldCoordsPose
+        wpsi = epsi;
+      }
+    }
+    if (t == 0) {
+      P.out_poses[3 * scan + 0] = wx;
+      P.out_poses[3 * scan + 1] = wy;
+      P.out_poses[3 * scan + 2] = wpsi;
+      if (P.out_cov && n > 0) {  // covMatrix = H, ScanMatcher.h:184; untouched for an empty scan (:68,189)
+        float* c = P.out_cov + 9 * (size_t)scan;
+        c[0] = last.h00; c[1] = last.h01; c[2] = last.h02;
+        c[3] = last.h01; c[4] = last.h11; c[5] = last.h12;
+        c[6] = last.h02; c[7] = last.h12; c[8] = last.h22;
+      }
+    }
+    if (cap > 0) group_sync(1 + g, GT);  // everyone done with spts before the next bulk copy lands
+  }
+}
+
+// Single evaluation (the getCompleteHessianDerivs seam): one CTA of 256 threads.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    hessian_kernel(const HsbLevelDev L, const float2* __restrict__ pts, int n, float px, float py, float ppsi,
+                   float* __restrict__ out12) {
+  __shared__ float red[8][12];
+  double sd, cd;
+  sincos((double)ppsi, &sd, &cd);
+  const float cs = (float)cd, ss = (float)sd;
+  Acc a;
+  acc_zero(a);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float2 p = pts[i];
+    eval_point<MODE>(L, p.x, p.y, cs, ss, px, py, a);
+  }
+  warp_reduce(a);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[w][0] = a.h00; red[w][1] = a.h11; red[w][2] = a.h22; red[w][3] = a.h01; red[w][4] = a.h02;
+    red[w][5] = a.h12; red[w][6] = a.d0;  red[w][7] = a.d1;  red[w][8] = a.d2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s[9];
+    for (int k = 0; k < 9; ++k) {
+      float v = 0.f;
+      for (int j = 0; j < 8; ++j) v += red[j][k];
+      s[k] = v;
+    }
+    // H row-major, then dTr
+    out12[0] = s[0]; out12[1] = s[3]; out12[2] = s[4];
+    out12[3] = s[3]; out12[4] = s[1]; out12[5] = s[5];
+    out12[6] = s[4]; out12[7] = s[5]; out12[8] = s[2];
+    out12[9] = s[6]; out12[10] = s[7]; out12[11] = s[8];
+  }
+}
+
+}  // namespace hsb
+#endif

@@ -1,0 +1,183 @@
+/* hector_slam_b200.h — C-ABI of the B200-native scan matcher / map writer.
+ *
+ * This is the drop-in boundary for hector_mapping's hot path.  The reference has no FFI of its
+ * own: its seam is the pure-virtual C++ class hectorslam::MapRepresentationInterface
+ * (hector_mapping/include/hector_slam_lib/slam_main/MapRepresentationInterface.h:38-62), whose
+ * only implementation, MapRepMultiMap, is created at slam_main/HectorSlamProcessor.h:58.  Each
+ * entry point below replaces one virtual of that interface (or one function the matcher is built
+ * from) and says which.  The host-side adaptor that plugs these calls back into the reference
+ * (class MapRepB200 : public hectorslam::MapRepresentationInterface) is
+ * hector_slam_b200/host/MapRepB200.h; INTEGRATION.md shows the three-line change a maintainer
+ * makes.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types; every call returns an hsb_status
+ *     (0 = ok, < 0 = error) and never throws; hsb_last_error() gives a message.
+ *   - poses are (x [m], y [m], psi [rad]) in the world frame, float32            (Eigen::Vector3f)
+ *   - scan endpoints are n x 2 float32, interleaved x,y, robot frame, in LEVEL-0 CELL units
+ *     (metres * hsb_get_scale_to_map()) — exactly DataContainer's memory layout
+ *     (scan/DataPointContainer.h:92-96; filled at src/HectorMappingRos.cpp:501-502,538)
+ *   - 3x3 matrices are 9 float32; H is symmetric so row/column order is moot.
+ *   - "host" entry points take host pointers and return when the result is in the output
+ *     buffers; "_device" entry points take device pointers and a CUDA stream (cudaStream_t cast
+ *     to void*) and are asynchronous on that stream.
+ *   - a handle is single-writer, like the reference (one spinner thread calls update()).
+ *   - numerical edge cases keep the reference's silent semantics: empty scan -> pose = hint and
+ *     the covariance buffer is left untouched (ScanMatcher.h:68,189); H(0,0)==0 or H(1,1)==0 ->
+ *     the Gauss-Newton step is skipped (ScanMatcher.h:201); endpoints outside [0, S-2] add
+ *     nothing (OccGridMapUtil.h:290-292); beams leaving the grid are dropped
+ *     (OccGridMapBase.h:176,186).  One deliberate difference: a NON-FINITE map coordinate is
+ *     treated as out of map instead of indexing memory with it (the reference crashes there,
+ *     SURVEY.md Q4).
+ */
+#ifndef HECTOR_SLAM_B200_H
+#define HECTOR_SLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSB_MAX_LEVELS 8
+
+typedef struct hsb_handle hsb_handle;
+
+typedef enum hsb_status {
+  HSB_OK = 0,
+  HSB_ERR_INVALID_ARG = -1,
+  HSB_ERR_CUDA = -2,
+  HSB_ERR_OUT_OF_MEMORY = -3,
+  HSB_ERR_NO_DEVICE = -4,
+  HSB_ERR_UNSUPPORTED = -5
+} hsb_status;
+
+/* How the four probability cells under an endpoint are fetched by the match kernel. */
+typedef enum hsb_gather_mode {
+  HSB_GATHER_AUTO = 0,
+  HSB_GATHER_LDG = 1,    /* four 32-bit loads from the linear probability plane              */
+  HSB_GATHER_TEX = 2     /* one tex2Dgather on a block-linear CUDA array (point-sampled 2x2) */
+} hsb_gather_mode;
+
+/* Constructor arguments of HectorSlamProcessor / MapRepMultiMap
+ * (slam_main/HectorSlamProcessor.h:54, slam_main/MapRepMultiMap.h:48). */
+typedef struct hsb_config {
+  float map_resolution;   /* level-0 cell length [m]                                        */
+  int   map_size_x;       /* level-0 cells; level k has size >> k (MapRepMultiMap.h:67)     */
+  int   map_size_y;
+  float start_x;          /* startCoords: where world (0,0) sits in the map, as a fraction  */
+  float start_y;
+  int   levels;           /* multi_res_size, 1..HSB_MAX_LEVELS                              */
+  int   device;           /* CUDA device ordinal                                            */
+  /* maxIterations handed to ScanMatcher::matchData per level (the matcher then runs
+   * maxIterations + 1 evaluations, ScanMatcher.h:74,94).  A zero entry selects the reference's
+   * literal: 5 at level 0, 3 at coarser levels (MapRepMultiMap.h:125,128). Use -1 for "0". */
+  int   max_iterations[HSB_MAX_LEVELS];
+  float update_factor_free;      /* 0 -> 0.4 (GridMapLogOdds.h:117)                         */
+  float update_factor_occupied;  /* 0 -> 0.6 (GridMapLogOdds.h:118); the ROS node sets 0.9  */
+  int   gather_mode;             /* hsb_gather_mode                                         */
+  int   reserved[7];
+} hsb_config;
+
+/* ---- lifetime -------------------------------------------------------------------------------*/
+/* new MapRepMultiMap(...) — slam_main/MapRepMultiMap.h:48-72.  All level planes are allocated in
+ * HBM and cleared (log-odds 0, probability 0.5). */
+int hsb_create(const hsb_config* cfg, hsb_handle** out);
+/* ~MapRepMultiMap — slam_main/MapRepMultiMap.h:74-81 */
+int hsb_destroy(hsb_handle* h);
+/* MapRepresentationInterface::reset — MapRepMultiMap.h:83-90 (every level cleared) */
+int hsb_reset(hsb_handle* h);
+/* setUpdateFactorFree / setUpdateFactorOccupied — MapRepMultiMap.h:149-167 */
+int hsb_set_update_factor_free(hsb_handle* h, float factor);
+int hsb_set_update_factor_occupied(hsb_handle* h, float factor);
+/* the two log-odds increments currently in force: out[0] = free, out[1] = occupied */
+int hsb_get_logodds_increments(hsb_handle* h, float out[2]);
+
+/* ---- getters --------------------------------------------------------------------------------*/
+/* getScaleToMap — MapRepMultiMap.h:92 ; getMapLevels — :94 */
+float hsb_get_scale_to_map(const hsb_handle* h);
+int   hsb_get_map_levels(const hsb_handle* h);
+/* dimensions and cell length of one level (GridMapBase::getSizeX/getSizeY/getCellLength) */
+int   hsb_get_level_info(const hsb_handle* h, int level, int* size_x, int* size_y, float* cell_length);
+/* GridMapBase::getMapCoordsPose / getWorldCoordsPose — map/GridMapBase.h:226-239 (host arithmetic,
+ * the same the kernels use) */
+int   hsb_map_coords_pose(const hsb_handle* h, int level, const float world[3], float out[3]);
+int   hsb_world_coords_pose(const hsb_handle* h, int level, const float map[3], float out[3]);
+
+/* ---- the hot path: matching -----------------------------------------------------------------*/
+/* MapRepresentationInterface::matchData — MapRepMultiMap.h:116-132: coarse-to-fine Gauss-Newton
+ * over all levels, on the device without a host round trip.  `cov_inout` receives the Hessian of
+ * the last evaluation (ScanMatcher.h:184) and is left untouched for n == 0.  The scan is also
+ * remembered as "the containers of the last match", which hsb_update_by_scan uses for the
+ * coarse levels exactly like MapRepMultiMap.h:143 does. `origo` may be NULL (= 0,0). */
+int hsb_match_data(hsb_handle* h, const float begin_estimate_world[3], const float* points_xy, int n,
+                   const float origo[2], float out_pose_world[3], float cov_inout[9]);
+
+/* B independent matchData calls against the current (frozen) map: scan b is
+ * points_xy[offsets[b] .. offsets[b+1]) with hint hints[3b..3b+2].  If `offsets` is NULL every
+ * item uses the one scan points_xy[0 .. n_shared) (pose-hypothesis mode).  Outputs: out_poses
+ * B x 3, out_cov B x 9 (may be NULL).  Host buffers (pinned memory lets the copies overlap the
+ * kernel).  Does not touch the "last match" containers. */
+int hsb_match_batch(hsb_handle* h, int B, const float* hints_world, const float* points_xy, const int* offsets,
+                    int n_shared, float* out_poses_world, float* out_cov);
+
+/* Same with everything resident in device memory; asynchronous on `stream`.  `total_points` is
+ * offsets[B] (ignored in shared-scan mode). */
+int hsb_match_batch_device(hsb_handle* h, int B, const float* d_hints_world, const float* d_points_xy,
+                           const int* d_offsets, int n_shared, int max_points_per_scan, float* d_out_poses_world,
+                           float* d_out_cov, void* stream);
+
+/* OccGridMapUtil::getCompleteHessianDerivs — map/OccGridMapUtil.h:64-104, one evaluation on one
+ * level: `pose_map` and `points_level_xy` are in that level's cell units.  This is the finest
+ * seam: the reference's own ScanMatcher can drive it one evaluation at a time. */
+int hsb_hessian_derivs(hsb_handle* h, int level, const float pose_map[3], const float* points_level_xy, int n,
+                       float H_out[9], float dTr_out[3]);
+
+/* ---- the hot path: map writing --------------------------------------------------------------*/
+/* MapRepresentationInterface::updateByScan — MapRepMultiMap.h:134-147 -> OccGridMapBase.h:121-168:
+ * Bresenham free/occupied log-odds update of every level, once per cell per scan.  Level 0 uses
+ * the scan given here; level k > 0 uses the scan of the last hsb_match_data scaled by 2^-k
+ * (MapRepMultiMap.h:143).  The probability planes of the touched cells are refreshed in the same
+ * pass. */
+int hsb_update_by_scan(hsb_handle* h, const float* points_xy, int n, const float origo[2],
+                       const float robot_pose_world[3]);
+/* OccGridMapBase::updateByScan on ONE level with that level's own container (points/origo in the
+ * level's cell units) — map/OccGridMapBase.h:121-168. */
+int hsb_update_level_by_scan(hsb_handle* h, int level, const float* points_level_xy, int n,
+                             const float origo_level[2], const float robot_pose_world[3]);
+/* MapRepresentationInterface::onMapUpdated — MapRepMultiMap.h:107-114.  The reference bumps its
+ * probability-cache epoch here; on the device the probability planes are already current, so this
+ * only orders the stream (kept so the host façade reads like the reference). */
+int hsb_on_map_updated(hsb_handle* h);
+
+/* ---- map planes (checkpoint / parity / replication) -----------------------------------------*/
+/* log-odds plane of one level, row-major [size_y][size_x] float32 (GridMapBase.h:141-149).
+ * Upload refreshes that level's probability plane. */
+int hsb_upload_level(hsb_handle* h, int level, const float* logodds_host);
+int hsb_download_level(hsb_handle* h, int level, float* logodds_host_out);
+/* probability plane P = e^l / (e^l + 1) (GridMapLogOdds.h:163-166) as the match kernel sees it */
+int hsb_download_prob(hsb_handle* h, int level, float* prob_host_out);
+/* device address of the level's log-odds plane (for NCCL broadcast of map replicas) and a full
+ * recompute of the probability planes after such an external write */
+void* hsb_level_logodds_device_ptr(hsb_handle* h, int level);
+int hsb_refresh_level(hsb_handle* h, int level, void* stream);
+
+/* ---- diagnostics ----------------------------------------------------------------------------*/
+const char* hsb_last_error(const hsb_handle* h);
+const char* hsb_status_string(int status);
+/* number of CUDA kernels this handle has launched since creation (bench.py's gpu_launches) */
+uint64_t hsb_get_launch_count(const hsb_handle* h);
+/* the gather mode actually in use (after HSB_GATHER_AUTO resolution) */
+int hsb_get_gather_mode(const hsb_handle* h);
+/* launch-shape knobs for experiments: "warps_per_scan" (0 = auto), "scans_per_block" (0 = auto),
+ * "stage_smem" (1 = stage scan endpoints in shared memory), "chunk" (scans per pipeline chunk of
+ * hsb_match_batch, 0 = auto).  Results never depend on them beyond summation order. */
+int hsb_set_tuning(hsb_handle* h, const char* key, int value);
+/* library build identification, e.g. "hector_slam_b200 0.1 sm_100a" */
+const char* hsb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HECTOR_SLAM_B200_H */

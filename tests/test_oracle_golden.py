@@ -1,0 +1,173 @@
+"""CPU: the oracles against the golden vectors generated from the compiled reference
+(oracle/gen_golden.py).  The plain-C port must reproduce them BIT FOR BIT; where the compiled
+reference itself is present (oracle/_ref) it is re-run too, which also guards the fixtures."""
+import numpy as np
+import pytest
+
+from conftest import apply_diff, golden_planes, load_golden
+
+
+def make(pyoracle, kind, g):
+    o = pyoracle.Oracle(kind, float(g["res"]), int(g["size"]), int(g["levels"]))
+    if "factors" in g.files:
+        o.set_update_factors(float(g["factors"][0]), float(g["factors"][1]))
+    return o
+
+
+def set_planes(o, planes):
+    for l, p in enumerate(planes):
+        o.set_logodds(l, p)
+
+
+@pytest.mark.parametrize("name", ["match3.npz", "match1.npz"])
+def test_match_goldens_bit_exact(pyoracle, oracle_kinds, name):
+    g = load_golden(name)
+    for kind in oracle_kinds:
+        o = make(pyoracle, kind, g)
+        set_planes(o, golden_planes(g))
+        for k in range(g["scans"].shape[0]):
+            p, c = o.match(g["hints"][k], g["scans"][k])
+            assert np.array_equal(p, g["ref_poses"][k]), (kind, k)
+            assert np.array_equal(c.reshape(9), g["ref_cov"][k]), (kind, k)
+        # matches land within 1.5 cm / 2 mrad of the synthetic ground truth (noise sigma 1 cm)
+        assert np.abs(g["ref_poses"][:, :2] - g["truth"][:, :2]).max() < 0.015
+        o.close()
+
+
+def test_three_evaluation_variant(pyoracle, oracle_kinds):
+    """BASELINE.json config 1's "3 GN iters": ScanMatcher::matchData(maxIterations=2)."""
+    g = load_golden("match1.npz")
+    for kind in oracle_kinds:
+        o = make(pyoracle, kind, g)
+        set_planes(o, golden_planes(g))
+        for k in range(g["scans"].shape[0]):
+            p, c = o.match_level(0, g["hints"][k], g["scans"][k], 2)
+            assert np.array_equal(p, g["ref_poses_3eval"][k])
+            assert np.array_equal(c.reshape(9), g["ref_cov_3eval"][k])
+        o.close()
+
+
+def test_per_evaluation_hessians(pyoracle, oracle_kinds):
+    g = load_golden("match3.npz")
+    for kind in oracle_kinds:
+        o = make(pyoracle, kind, g)
+        set_planes(o, golden_planes(g))
+        for i in range(len(g["ev_level"])):
+            l, k = int(g["ev_level"][i]), int(g["ev_scan"][i])
+            pts = (g["scans"][k] * np.float32(2.0 ** -l)).astype(np.float32)
+            H, d = o.hessian_derivs(l, g["ev_pose"][i], pts)
+            assert np.array_equal(H.reshape(9), g["ev_H"][i])
+            assert np.array_equal(d, g["ev_dTr"][i])
+        # pose conversions (GridMapBase.h:226-239) and log-odds increments (GridMapLogOdds.h:187-203)
+        for k in range(4):
+            for l in range(3):
+                m = o.map_coords_pose(l, g["conv_world"][k])
+                assert np.array_equal(m, g["conv_map"][k, l])
+                assert np.array_equal(o.world_coords_pose(l, m), g["conv_back"][k, l])
+        assert np.array_equal(o.logodds_increments(), g["increments"])
+        assert np.allclose(g["increments"], [-0.405465156, 2.19722438], rtol=0, atol=1e-7)
+        o.close()
+
+
+def test_interpolation_bounds_and_single_steps(pyoracle, oracle_kinds):
+    g = load_golden("interp.npz")
+    for kind in oracle_kinds:
+        o = pyoracle.Oracle(kind, float(g["res"]), int(g["size"]), int(g["levels"]))
+        for l in range(int(g["levels"])):
+            o.set_logodds(l, g[f"plane{l}"])
+            assert np.array_equal(o.get_prob(l), g[f"prob{l}"])
+        for i in range(len(g["ev_level"])):
+            l = int(g["ev_level"][i])
+            H, d = o.hessian_derivs(l, g["ev_pose"][i], g["ev_pts"][i])
+            assert np.array_equal(H.reshape(9), g["ev_H"][i])
+            assert np.array_equal(d, g["ev_dTr"][i])
+            p, _ = o.match_level(l, g["step_hint"][i], g["ev_pts"][i], 0)
+            assert np.array_equal(p, g["step_pose"][i])
+        o.close()
+    # the fixtures do exercise the rotation clamp (ScanMatcher.h:209-215)
+    dpsi = g["step_pose"][:, 2] - g["step_hint"][:, 2]
+    assert np.sum(g["step_clamped"]) >= 3
+    assert np.all(np.abs(np.abs(dpsi[g["step_clamped"]]) - 0.2) < 1e-5)
+
+
+def test_map_update_goldens(pyoracle, oracle_kinds):
+    g = load_golden("match3.npz")
+    for kind in oracle_kinds:
+        o = make(pyoracle, kind, g)
+        base = golden_planes(g)
+        set_planes(o, base)
+        o.match(g["hints"][0], g["scans"][0])
+        o.update_by_scan(g["scans"][0], g["upd1_pose"])
+        o.on_map_updated()
+        want1 = apply_diff(base, g, "upd1")
+        for l in range(3):
+            assert np.array_equal(o.get_logodds(l), want1[l]), (kind, l)
+        o.match(g["hints"][1], g["scans"][1])
+        o.update_by_scan(g["scans"][2], g["upd2_pose"])
+        o.on_map_updated()
+        want2 = apply_diff(want1, g, "upd2")
+        for l in range(3):
+            assert np.array_equal(o.get_logodds(l), want2[l]), (kind, l)
+        p, c = o.match(g["hints"][3], g["scans"][3])
+        assert np.array_equal(p, g["after_upd_pose"])
+        assert np.array_equal(c.reshape(9), g["after_upd_cov"])
+        o.close()
+
+
+def test_edge_cases(pyoracle, oracle_kinds):
+    g = load_golden("match1.npz")
+    for kind in oracle_kinds:
+        o = make(pyoracle, kind, g)
+        set_planes(o, golden_planes(g))
+        cov_in = np.arange(9, dtype=np.float32)
+        p, c = o.match(g["hints"][0], np.zeros((0, 2), np.float32), cov_in=cov_in)
+        assert np.array_equal(p, g["hints"][0]) and np.array_equal(c.reshape(9), cov_in)  # ScanMatcher.h:68,189
+        far = (g["scans"][0] + np.float32(1e5)).astype(np.float32)
+        p, c = o.match(g["hints"][0], far)
+        assert np.array_equal(p, g["edge_far_pose"]) and np.all(c == 0)
+        assert np.abs(p - g["hints"][0]).max() < 1e-5  # only the world->map->world round trip
+        o.close()
+
+
+def test_slam_run_matches_golden(pyoracle, oracle_kinds):
+    """HectorSlamProcessor::update over a short trajectory starting on an empty map (Q12)."""
+    g = load_golden("slam3.npz")
+    for kind in oracle_kinds:
+        o = make(pyoracle, kind, g)
+        o.set_map_update_thresholds(0.0, 0.0)
+        hint = g["first_hint"]
+        for k in range(g["scans"].shape[0]):
+            pose, _ = o.update(g["scans"][k], hint)
+            assert np.array_equal(pose, g["est"][k]), (kind, k)
+            hint = pose
+        final = golden_planes(g, "final")
+        for l in range(3):
+            assert np.array_equal(o.get_logodds(l), final[l])
+        assert np.abs(g["est"][:, :2] - g["traj"][:, :2]).max() < 0.02
+        o.close()
+
+
+def test_port_equals_reference_on_fresh_inputs(pyoracle, oracle_kinds):
+    """Beyond the fixtures: a fresh seeded world, both oracles, bit-for-bit (needs oracle/_ref)."""
+    if "reference" not in oracle_kinds:
+        pytest.skip("compiled reference (oracle/_ref/libhsref.so) not present")
+    from hector_slam_b200 import synth
+
+    world = synth.World(1, seed=77)
+    rng = np.random.default_rng(3)
+    poses = world.sample_free_poses(24, rng)
+    pts, offs = synth.make_scan_batch(world, poses, noise_seed=9)
+    hints = synth.perturb_hints(poses, seed=4)
+    res = []
+    for kind in ("reference", "port"):
+        o = pyoracle.Oracle(kind, 0.05, 1024, 3)
+        o.set_update_factors(0.4, 0.9)
+        pyoracle.build_map_known_poses(o, world)
+        P, Cv, _ = o.match_batch(hints, pts, offs, nthreads=1)
+        P2, _, _ = o.match_batch(hints, pts, offs, nthreads=3)
+        assert np.array_equal(P, P2)
+        res.append((P, Cv, [o.get_logodds(l) for l in range(3)]))
+        o.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    for l in range(3):
+        assert np.array_equal(res[0][2][l], res[1][2][l])
