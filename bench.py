@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="print throughput for launch shapes / gather modes and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nbuf", type=int, default=8, help="distinct input batches cycled through (inputs > L2)")
+    ap.add_argument("--shapes", default="", help="sweep only these 'W,G,stage;...' launch shapes")
+    ap.add_argument("--sweep-iters", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -272,26 +274,30 @@ def main():
                                d_poses.data_ptr(), d_cov.data_ptr(), stream)
 
     if args.sweep:
-        for mode in ("ldg", "tex"):
+        shapes = [(1, 1), (1, 2), (1, 4), (1, 8), (2, 1), (2, 2), (2, 4), (4, 1), (4, 2), (8, 1), (16, 1)]
+        combos = [(w, g, st) for st in (1, 0) for (w, g) in shapes]
+        if args.shapes:
+            combos = [tuple(int(x) for x in c.split(",")) for c in args.shapes.split(";") if c]
+        for mode in (("ldg", "tex") if args.gather == "auto" else (args.gather,)):
             r2 = capi.MapRepB200(RES, MAP_SIZE, levels=LEVELS, device=local_rank, update_factor_free=0.4,
                                  update_factor_occupied=0.9, gather_mode={"ldg": 1, "tex": 2}[mode])
             for l in range(LEVELS):
                 r2.upload_level(l, planes_host[l])
-            for stage in (1, 0):
-                for (w, g) in ((1, 1), (1, 2), (1, 4), (1, 8), (2, 1), (2, 2), (2, 4), (4, 1), (4, 2), (8, 1), (16, 1)):
+            for (w, g, stage) in combos:
+                if True:
                     r2.set_tuning(warps_per_scan=w, scans_per_block=g, stage_smem=stage)
-                    for i in range(3):
+                    for i in range(min(3, args.sweep_iters)):
                         r2.match_batch_device(B, d_hints[0].data_ptr(), d_pts[0].data_ptr(), d_offs.data_ptr(), 0, N_PTS,
                                               d_poses.data_ptr(), d_cov.data_ptr(), stream)
                     torch.cuda.synchronize()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    for i in range(10):
+                    for i in range(args.sweep_iters):
                         r2.match_batch_device(B, d_hints[i % nbuf].data_ptr(), d_pts[i % nbuf].data_ptr(), d_offs.data_ptr(),
                                               0, N_PTS, d_poses.data_ptr(), d_cov.data_ptr(), stream)
                     e1.record()
                     torch.cuda.synchronize()
-                    ms = e0.elapsed_time(e1) / 10
+                    ms = e0.elapsed_time(e1) / args.sweep_iters
                     print(f"sweep mode={mode} stage={stage} W={w} G={g}: {ms:.3f} ms/step  {B / ms * 1e3 / 1e6:.2f} M matches/s",
                           flush=True)
             r2.close()

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libhsb200.so")
+LIB_PATH = os.environ.get("HSB_LIB_PATH") or os.path.join(_PKG, "lib", "libhsb200.so")
 HSB_MAX_LEVELS = 8
 
 GATHER_AUTO, GATHER_LDG, GATHER_TEX = 0, 1, 2

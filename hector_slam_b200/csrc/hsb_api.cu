@@ -193,6 +193,30 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
   if (smem > 48 * 1024) {
     HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  {
+    // Shared-memory carve-out: left alone the driver picks a small one for kernels that ask for a
+    // few hundred bytes, which then caps resident CTAs (measured: 7 CTAs/SM for 64-thread blocks).
+    // Ask for what full occupancy of this launch shape needs.
+    static int regs = 0;
+    if (!regs) {
+      cudaFuncAttributes fa;
+      HSB_CUDA(h, cudaFuncGetAttributes(&fa, kern));
+      regs = fa.numRegs > 0 ? fa.numRegs : 32;
+    }
+    const int threads = W * G * 32;
+    int blocks = 2048 / threads;
+    blocks = std::min(blocks, 32);
+    blocks = std::min(blocks, 65536 / (((regs + 7) / 8 * 8) * threads));
+    blocks = std::max(blocks, 1);
+    size_t need = (size_t)blocks * (smem + 1024);
+    int pct = (int)((need * 100 + 233471) / 233472);
+    pct = std::min(100, std::max(pct, 4));
+    static int last_pct = -1;
+    if (pct != last_pct) {
+      HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+      last_pct = pct;
+    }
+  }
   int grid = (P.B + G - 1) / G;
   kern<<<grid, W * G * 32, smem, st>>>(P);
   h->launches++;
@@ -224,13 +248,13 @@ int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t 
 int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   int W = h->tune_warps_per_scan, G = h->tune_scans_per_block;
   if (W <= 0) {
-    // enough warps to fill the chip: ~16 warps per SM
-    long want = ((long)h->sm_count * 16 + P.B - 1) / P.B;
+    // about 32 resident warps per SM: one warp per scan for big batches, a whole CTA for one scan
+    long want = ((long)h->sm_count * 32 + P.B - 1) / P.B;
     W = 1;
     while (W < want && W < 32) W *= 2;
-    if (W == 32 && max_n <= 17 * 64 && max_n > 1024) W = 17;  // 1081-pt scan: 2 points per lane
+    if (W == 32 && max_n <= 17 * 64 && max_n > 1024) W = 17;  // 1081-pt scan: exactly 2 points per lane
   }
-  if (G <= 0) G = (W >= 4) ? 1 : 4 / W;
+  if (G <= 0) G = 1;
   if (h->gather_mode == HSB_GATHER_TEX) return launch_match_mode<hsb::MODE_TEX>(h, P, max_n, st, W, G);
   return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G);
 }
@@ -332,7 +356,7 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
   for (int i = 0; i < 4; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
   HSB_CUDA_C(cudaMallocHost(&h->h_pin, 64 * sizeof(float)));
 
-  h->gather_mode = cfg->gather_mode == HSB_GATHER_TEX ? HSB_GATHER_TEX : HSB_GATHER_LDG;
+  h->gather_mode = cfg->gather_mode == HSB_GATHER_LDG ? HSB_GATHER_LDG : HSB_GATHER_TEX;  // AUTO -> TEX (measured faster)
   float ffree = cfg->update_factor_free > 0.f ? cfg->update_factor_free : 0.4f;      // GridMapLogOdds.h:117
   float focc = cfg->update_factor_occupied > 0.f ? cfg->update_factor_occupied : 0.6f;  // :118
   h->log_odds_free = prob_to_log_odds(ffree);

@@ -78,56 +78,180 @@ __device__ __forceinline__ void solve3(const Acc& s, float& o0, float& o1, float
   o2 = __fadd_rn(__fmul_rn(i20, s.d0), __fadd_rn(__fmul_rn(i21, s.d1), __fmul_rn(i22, s.d2)));
 }
 
-// One endpoint of one evaluation: OccGridMapUtil.h:76-98 with :287-347 inlined.
-//   cs, ss : cos/sin of the pose angle, pre-multiplied by the level's point scale 2^-k (exact,
-//            so (cs*px) equals the reference's c * (px * 2^-k) bit for bit)
-//   x, y   : pose translation in level cells
+// ---- one batch of U endpoints of one evaluation ------------------------------------------------
+// OccGridMapUtil.h:76-98 with interpMapValueWithDerivatives (:287-347) inlined, restructured so
+// that the U gathers of a batch are all in flight before the first one is consumed (branch-free
+// address phase, predicated accumulate phase).
+//
+// Rounding.  Measured on B200 against the oracle (scripts/parity_probe.py): the summation ORDER
+// of H/dTr does not move the result (the Gauss-Newton fixed point is reached bit-identically),
+// but the rounding of the map coordinate q = T*p does — q is ~1e3 cells, so one ulp of q is
+// ~6e-5 of a cell in the interpolation weights.  q is therefore computed with the oracle's exact
+// operation sequence (oracle/hs_oracle.c affine2_apply: m[0]*px + (m[1]*py + m[2]), four products
+// shared with rotDeriv), every operation rounded separately.  HSB_FP_VARIANT selects how the rest
+// is evaluated: 0 = every operation as the oracle (no contraction anywhere), 1 = the reference's
+// formulas with FMA contraction allowed, 2 = algebraically regrouped bilinear form (fewest ops).
+#ifndef HSB_FP_VARIANT
+#define HSB_FP_VARIANT 2
+#endif
+#ifndef HSB_UNROLL
+#define HSB_UNROLL 4
+#endif
+
+struct PointPre {
+  float rx, ry;   // rotated endpoint = d(q)/d(psi) terms: rotDeriv = rx*gy - ry*gx
+  float fx, fy;   // interpolation weights
+  float cx, cy;   // texture coordinates (MODE_TEX)
+  int idx;        // cell index (MODE_LDG)
+  bool inside;
+};
+
+// The few per-level constants the inner loop touches, copied to registers once per level (indexing
+// the __grid_constant__ array with a runtime level inside the loop costs a constant-bank load each).
+struct LevelRegs {
+  float lim_x, lim_y;
+  cudaTextureObject_t tex;
+  const float* prob;
+  int sx;
+};
+__device__ __forceinline__ LevelRegs level_regs(const HsbLevelDev& L) {
+  LevelRegs r;
+  r.lim_x = L.lim_x;
+  r.lim_y = L.lim_y;
+  r.tex = L.tex;
+  r.prob = L.prob;
+  r.sx = L.sx;
+  return r;
+}
+
 template <int MODE>
-__device__ __forceinline__ void eval_point(const HsbLevelDev& L, float px, float py, float cs, float ss, float x, float y,
-                                           Acc& a) {
-  // T * p with T = Translation(x,y) * Rotation(psi) (OccGridMapUtil.h:80,349-352)
-  const float rx = cs * px - ss * py;  // rotated endpoint (also d(q)/d(psi) terms below)
-  const float ry = ss * px + cs * py;
-  const float qx = rx + x;
-  const float qy = ry + y;
-  // pointOutOfMapBounds, MapDimensionProperties.h:65-68; written so that NaN is OUT (the
-  // reference lets NaN through and then indexes with it — SURVEY.md Q4)
-  const bool inside = (qx >= 0.0f) && (qx <= L.lim_x) && (qy >= 0.0f) && (qy <= L.lim_y);
-  if (!inside) return;  // value 0, gradient 0: contributes nothing (OccGridMapUtil.h:290-292)
-  const int ix = (int)qx, iy = (int)qy;                   // :295
-  const float fx = qx - (float)ix, fy = qy - (float)iy;   // :298
-  float i0, i1, i2, i3;
+__device__ __forceinline__ void point_address(const LevelRegs& L, float px, float py, bool valid, float cs, float ss,
+                                              float x, float y, PointPre& o) {
+  // cs, ss carry the level's 2^-k point scale (exact), so cs*px == c*(px*2^-k) bit for bit
+  const float m1 = __fmul_rn(cs, px), m2 = __fmul_rn(ss, py), m3 = __fmul_rn(ss, px), m4 = __fmul_rn(cs, py);
+  const float qx = __fadd_rn(m1, __fadd_rn(-m2, x));   // OccGridMapUtil.h:80
+  const float qy = __fadd_rn(m3, __fadd_rn(m4, y));
+  o.rx = __fsub_rn(m1, m2);                            // cosRot*px - sinRot*py   (:87)
+  o.ry = __fadd_rn(m3, m4);                            // -( -sinRot*px - cosRot*py )
+  // pointOutOfMapBounds, MapDimensionProperties.h:65-68, written so that NaN is OUT (the
+  // reference lets NaN through and then indexes memory with it — SURVEY.md Q4)
+  o.inside = valid && (qx >= 0.0f) && (qx <= L.lim_x) && (qy >= 0.0f) && (qy <= L.lim_y);
   if (MODE == MODE_TEX) {
-    // point-sampled 2x2 footprint: texel centres (ix, iy)..(ix+1, iy+1); coordinates are exact
-    // half-integers + 0.5 so the unit's fixed-point conversion cannot pick a neighbour
-    const float4 g = tex2Dgather<float4>(L.tex, (float)ix + 1.0f, (float)iy + 1.0f, 0);
-    i0 = g.w;  // (ix  , iy  )
-    i1 = g.z;  // (ix+1, iy  )
-    i2 = g.x;  // (ix  , iy+1)
-    i3 = g.y;  // (ix+1, iy+1)
+    // floor == trunc on the valid domain (:295); one FRND instead of F2I + I2F
+    const float flx = truncf(qx), fly = truncf(qy);
+    o.fx = __fsub_rn(qx, flx);                         // :298
+    o.fy = __fsub_rn(qy, fly);
+    // texel centres (ix,iy)..(ix+1,iy+1): integer + 1.0 is exact in the unit's fixed-point
+    // coordinate conversion, so it cannot select a neighbouring footprint; clamp addressing makes
+    // any coordinate (also garbage from an outside point) safe
+    o.cx = flx + 1.0f;
+    o.cy = fly + 1.0f;
   } else {
-    const float* p = L.prob + (size_t)iy * (size_t)L.sx + (size_t)ix;  // :302
-    i0 = __ldg(p);
-    i1 = __ldg(p + 1);
-    i2 = __ldg(p + L.sx);
-    i3 = __ldg(p + L.sx + 1);
+    const int ix = (int)qx, iy = (int)qy;              // :295 (garbage but harmless when !inside)
+    o.fx = __fsub_rn(qx, (float)ix);
+    o.fy = __fsub_rn(qy, (float)iy);
+    o.idx = o.inside ? iy * L.sx + ix : 0;             // :302
   }
+}
+
+template <int MODE>
+__device__ __forceinline__ float4 point_fetch(const LevelRegs& L, const PointPre& p) {
+  float4 v;  // (i0, i1, i2, i3) = cells (ix,iy) (ix+1,iy) (ix,iy+1) (ix+1,iy+1)
+  if (MODE == MODE_TEX) {
+    const float4 g = tex2Dgather<float4>(L.tex, p.cx, p.cy, 0);
+    v = make_float4(g.w, g.z, g.x, g.y);
+  } else {
+    const float* c = L.prob + p.idx;
+    v = make_float4(__ldg(c), __ldg(c + 1), __ldg(c + L.sx), __ldg(c + L.sx + 1));
+  }
+  return v;
+}
+
+__device__ __forceinline__ void point_accumulate(const PointPre& p, const float4 v, Acc& a) {
+  const float i0 = v.x, i1 = v.y, i2 = v.z, i3 = v.w, fx = p.fx, fy = p.fy;
+#if HSB_FP_VARIANT == 0
+  const float xi = __fsub_rn(1.0f, fx), yi = __fsub_rn(1.0f, fy);
+  const float m = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(i0, xi), __fmul_rn(i1, fx)), yi),
+                            __fmul_rn(__fadd_rn(__fmul_rn(i2, xi), __fmul_rn(i3, fx)), fy));   // :342-343
+  const float gx = -__fadd_rn(__fmul_rn(__fsub_rn(i0, i1), xi), __fmul_rn(__fsub_rn(i2, i3), fx));  // :344
+  const float gy = -__fadd_rn(__fmul_rn(__fsub_rn(i0, i2), yi), __fmul_rn(__fsub_rn(i1, i3), fy));  // :345
+  const float f = __fsub_rn(1.0f, m);                                                          // :82
+  const float r = __fadd_rn(__fmul_rn(-p.ry, gx), __fmul_rn(p.rx, gy));                        // :87
+  if (p.inside) {
+    a.d0 = __fadd_rn(a.d0, __fmul_rn(gx, f));
+    a.d1 = __fadd_rn(a.d1, __fmul_rn(gy, f));
+    a.d2 = __fadd_rn(a.d2, __fmul_rn(r, f));
+    a.h00 = __fadd_rn(a.h00, __fmul_rn(gx, gx));
+    a.h11 = __fadd_rn(a.h11, __fmul_rn(gy, gy));
+    a.h22 = __fadd_rn(a.h22, __fmul_rn(r, r));
+    a.h01 = __fadd_rn(a.h01, __fmul_rn(gx, gy));
+    a.h02 = __fadd_rn(a.h02, __fmul_rn(gx, r));
+    a.h12 = __fadd_rn(a.h12, __fmul_rn(gy, r));
+  }
+#else
+#if HSB_FP_VARIANT == 1
   const float xi = 1.0f - fx, yi = 1.0f - fy;
-  const float m = (i0 * xi + i1 * fx) * yi + (i2 * xi + i3 * fx) * fy;  // :342-343
-  const float gx = -((i0 - i1) * xi + (i2 - i3) * fx);                  // :344 (x-weights, as the reference)
-  const float gy = -((i0 - i2) * yi + (i1 - i3) * fy);                  // :345
-  const float f = 1.0f - m;                                             // :82
-  // rotDeriv = (-sin*px - cos*py)*gx + (cos*px - sin*py)*gy = (-ry)*gx + rx*gy     :87
-  const float r = rx * gy - ry * gx;
-  a.d0 += gx * f;
-  a.d1 += gy * f;
-  a.d2 += r * f;
-  a.h00 += gx * gx;
-  a.h11 += gy * gy;
-  a.h22 += r * r;
-  a.h01 += gx * gy;
-  a.h02 += gx * r;
-  a.h12 += gy * r;
+  const float m = (i0 * xi + i1 * fx) * yi + (i2 * xi + i3 * fx) * fy;
+  const float gx = -((i0 - i1) * xi + (i2 - i3) * fx);
+  const float gy = -((i0 - i2) * yi + (i1 - i3) * fy);
+#else
+  // bilinear form regrouped: d01 = i1-i0, d02 = i2-i0, dd = (i3-i2) - (i1-i0)
+  const float d01 = i1 - i0, d02 = i2 - i0, dd = (i3 - i2) - d01;
+  const float gx = fmaf(fx, dd, d01);            // = (i1-i0)(1-fx) + (i3-i2)fx
+  const float gy = fmaf(fy, dd, d02);            // = (i2-i0)(1-fy) + (i3-i1)fy
+  const float m = fmaf(fy, fmaf(fx, dd, d02), fmaf(fx, d01, i0));
+#endif
+  const float f = 1.0f - m;
+  const float r = p.rx * gy - p.ry * gx;
+  if (p.inside) {
+    a.d0 += gx * f;
+    a.d1 += gy * f;
+    a.d2 += r * f;
+    a.h00 += gx * gx;
+    a.h11 += gy * gy;
+    a.h22 += r * r;
+    a.h01 += gx * gy;
+    a.h02 += gx * r;
+    a.h12 += gy * r;
+  }
+#endif
+}
+
+// All endpoints i = first, first + stride, ... < n of one evaluation, U at a time: full batches
+// without bounds checks, then one guarded batch for the tail.
+template <int MODE, int U, typename PtsPtr>
+__device__ __forceinline__ void eval_points(const LevelRegs& L, PtsPtr pts, int first, int stride, int n, float cs, float ss,
+                                            float x, float y, Acc& a) {
+  int base = first;
+  const int last_full = n - (U - 1) * stride;  // base < last_full  =>  all U points exist
+  for (; base < last_full; base += U * stride) {
+    PointPre pre[U];
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float2 p = pts[base + u * stride];
+      point_address<MODE>(L, p.x, p.y, true, cs, ss, x, y, pre[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = point_fetch<MODE>(L, pre[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) point_accumulate(pre[u], v[u], a);
+  }
+  if (base < n) {
+    PointPre pre[U];
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * stride;
+      const bool valid = i < n;
+      const float2 p = pts[valid ? i : n - 1];
+      point_address<MODE>(L, p.x, p.y, valid, cs, ss, x, y, pre[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = point_fetch<MODE>(L, pre[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) point_accumulate(pre[u], v[u], a);
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -176,8 +300,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void group_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// Barrier among the W warps of group g.  The id must be an immediate: with a register operand
+// ptxas reserves all 16 named barriers for the CTA, and the SM's barrier budget then caps
+// residency at 4 CTAs (measured with ncu: launch__occupancy_limit_barriers).
+template <int W>
+__device__ __forceinline__ void group_sync(int g) {
+  if (W == 1) {
+    __syncwarp();
+    return;
+  }
+  switch (g) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"n"(W * 32) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"n"(W * 32) : "memory"); break;
+    case 3: asm volatile("bar.sync 4, %0;" ::"n"(W * 32) : "memory"); break;
+    case 4: asm volatile("bar.sync 5, %0;" ::"n"(W * 32) : "memory"); break;
+    case 5: asm volatile("bar.sync 6, %0;" ::"n"(W * 32) : "memory"); break;
+    case 6: asm volatile("bar.sync 7, %0;" ::"n"(W * 32) : "memory"); break;
+    default: asm volatile("bar.sync 8, %0;" ::"n"(W * 32) : "memory"); break;
+  }
 }
 
 // Shared-memory carve-up for G groups: [G] mbarriers | [G][2][W][12] reduction slots | points
@@ -220,8 +361,9 @@ __global__ void __launch_bounds__(W * G * 32)
       beg = 0;
       n = P.n_shared;
     }
-    const float2* gpts = P.pts + beg;
-    const float2* pts = gpts;
+    const float2* __restrict__ gpts = P.pts + beg;
+    const float2* spts_scan = spts;  // shared-memory copy of the scan (valid when staged)
+    bool staged = false;
     if (cap > 0 && n < cap && n > 0) {
       // Stage the scan into shared memory.  Point i goes to spts[i + head] where head = 1 iff the
       // scan starts on an odd point (8- but not 16-byte aligned), so that global and shared
@@ -243,8 +385,9 @@ __global__ void __launch_bounds__(W * G * 32)
         mbar_wait(mbar, phase);
         phase ^= 1u;
       }
-      group_sync(1 + g, GT);  // head/tail stores visible to the whole group
-      pts = sdst;
+      group_sync<W>(g);  // head/tail stores visible to the whole group
+      spts_scan = sdst;
+      staged = true;
     }
 
     float wx = P.hints[3 * scan + 0], wy = P.hints[3 * scan + 1], wpsi = P.hints[3 * scan + 2];
@@ -253,6 +396,7 @@ __global__ void __launch_bounds__(W * G * 32)
     if (n > 0) {
       for (int lvl = P.levels - 1; lvl >= 0; --lvl) {
         const HsbLevelDev& L = P.lv[lvl];
+        const LevelRegs LR = level_regs(L);
         float ex, ey, epsi = wpsi;
         affine_apply_exact(L.mtw, wx, wy, ex, ey);  // ScanMatcher.h:70 getMapCoordsPose
         for (int e = 0; e < L.evals; ++e) {          // ScanMatcher.h:74 + :94-97
@@ -261,11 +405,10 @@ __global__ void __launch_bounds__(W * G * 32)
           const float cs = (float)cd * L.pt_scale, ss = (float)sd * L.pt_scale;
           Acc a;
           acc_zero(a);
-#pragma unroll 4
-          for (int i = t; i < n; i += GT) {
-            const float2 p = pts[i];
-            eval_point<MODE>(L, p.x, p.y, cs, ss, ex, ey, a);
-          }
+          if (staged)
+            eval_points<MODE, HSB_UNROLL>(LR, spts_scan, t, GT, n, cs, ss, ex, ey, a);
+          else
+            eval_points<MODE, HSB_UNROLL>(LR, gpts, t, GT, n, cs, ss, ex, ey, a);
           warp_reduce(a);
           if (W > 1) {
             float* slot = red + (red_flip * W + w) * 12;
@@ -273,7 +416,7 @@ __global__ void __launch_bounds__(W * G * 32)
               slot[0] = a.h00; slot[1] = a.h11; slot[2] = a.h22; slot[3] = a.h01; slot[4] = a.h02;
               slot[5] = a.h12; slot[6] = a.d0;  slot[7] = a.d1;  slot[8] = a.d2;
             }
-            group_sync(1 + g, GT);
+            group_sync<W>(g);
             const float* base = red + red_flip * W * 12;
             acc_zero(a);
 #pragma unroll
@@ -304,14 +447,16 @@ __global__ void __launch_bounds__(W * G * 32)
       P.out_poses[3 * scan + 0] = wx;
       P.out_poses[3 * scan + 1] = wy;
       P.out_poses[3 * scan + 2] = wpsi;
-      if (P.out_cov && n > 0) {  // covMatrix = H, ScanMatcher.h:184; untouched for an empty scan (:68,189)
+      if (P.out_cov) {  // covMatrix = H, ScanMatcher.h:184.  An empty scan leaves the caller's matrix
+        // untouched in the reference (:68,189): hsb_match_data honours that on the host side, the
+        // batch entry points document a zero matrix instead (`last` is still zero then).
         float* c = P.out_cov + 9 * (size_t)scan;
         c[0] = last.h00; c[1] = last.h01; c[2] = last.h02;
         c[3] = last.h01; c[4] = last.h11; c[5] = last.h12;
         c[6] = last.h02; c[7] = last.h12; c[8] = last.h22;
       }
     }
-    if (cap > 0) group_sync(1 + g, GT);  // everyone done with spts before the next bulk copy lands
+    if (cap > 0) group_sync<W>(g);  // everyone done with spts before the next bulk copy lands
   }
 }
 
@@ -326,10 +471,7 @@ __global__ void __launch_bounds__(256)
   const float cs = (float)cd, ss = (float)sd;
   Acc a;
   acc_zero(a);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float2 p = pts[i];
-    eval_point<MODE>(L, p.x, p.y, cs, ss, px, py, a);
-  }
+  eval_points<MODE, HSB_UNROLL>(level_regs(L), pts, threadIdx.x, blockDim.x, n, cs, ss, px, py, a);
   warp_reduce(a);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) {

@@ -118,7 +118,9 @@ int hsb_match_data(hsb_handle* h, const float begin_estimate_world[3], const flo
  * points_xy[offsets[b] .. offsets[b+1]) with hint hints[3b..3b+2].  If `offsets` is NULL every
  * item uses the one scan points_xy[0 .. n_shared) (pose-hypothesis mode).  Outputs: out_poses
  * B x 3, out_cov B x 9 (may be NULL).  Host buffers (pinned memory lets the copies overlap the
- * kernel).  Does not touch the "last match" containers. */
+ * kernel).  Does not touch the "last match" containers.  An empty scan returns its hint as the
+ * pose and an all-zero out_cov entry (the batch buffer is write-only; the single-scan call above
+ * keeps the reference's "untouched" behaviour). */
 int hsb_match_batch(hsb_handle* h, int B, const float* hints_world, const float* points_xy, const int* offsets,
                     int n_shared, float* out_poses_world, float* out_cov);
 
