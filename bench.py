@@ -240,23 +240,9 @@ def main():
     # ---- map: built once on rank 0 through the product path, replicated with one NCCL broadcast
     if rank == 0:
         build_map_on_gpu(rep, world)
-    planes_dev = []
-    for l in range(LEVELS):
-        sx, sy, _ = rep.level_info(l)
+    from hector_slam_b200 import parallel
 
-        class _Wrap:  # zero-copy view of the handle's log-odds plane for torch / NCCL
-            __cuda_array_interface__ = {"shape": (sy, sx), "typestr": "<f4", "data": (rep.level_logodds_device_ptr(l), False),
-                                        "version": 2}
-
-        planes_dev.append(torch.as_tensor(_Wrap(), device=dev))
-    if world_size > 1:
-        for l in range(LEVELS):
-            dist.broadcast(planes_dev[l], src=0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            for l in range(LEVELS):
-                rep.refresh_level(l, 0)
-        torch.cuda.synchronize()
+    planes_dev = parallel.replicate_map(rep, dev, src=0)
     planes_host = [p.cpu().numpy() for p in planes_dev] if rank == 0 else None
 
     # ---- device-resident inputs: nbuf distinct copies so that a step's inputs are not L2-warm

@@ -1,0 +1,90 @@
+"""Multi-GPU plumbing: one process per GPU, `torch.distributed` (NCCL on the GPUs, gloo in the CPU
+tests).  The match path shards by scan / hypothesis and needs NO collective on the data path:
+every rank holds a replica of the map and matches its contiguous share.  Collectives appear only
+where the path has a real exchange: replicating the map (broadcast of the log-odds planes from the
+rank that owns / writes the map) and, optionally, assembling the result poses (all_gather).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous balanced partition of range(n): shard sizes differ by at most one."""
+    lo = (n * rank) // world
+    hi = (n * (rank + 1)) // world
+    return lo, hi
+
+
+def shard_scans(hints, pts, offsets, rank: int, world: int):
+    """This rank's contiguous share of a ragged scan batch, offsets rebased to zero."""
+    B = hints.shape[0]
+    lo, hi = shard_range(B, rank, world)
+    offsets = np.asarray(offsets)
+    p0, p1 = int(offsets[lo]), int(offsets[hi])
+    return hints[lo:hi], pts[p0:p1], (offsets[lo:hi + 1] - p0).astype(np.int32), (lo, hi)
+
+
+class _DevicePlane:
+    """Zero-copy torch view of a raw device plane (the handle owns the memory)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def level_plane_tensor(rep, level: int, device) -> torch.Tensor:
+    """The handle's log-odds plane of `level` as a torch CUDA tensor (no copy)."""
+    sx, sy, _ = rep.level_info(level)
+    return torch.as_tensor(_DevicePlane(rep.level_logodds_device_ptr(level), (sy, sx)), device=device)
+
+
+def broadcast_planes(planes: list[torch.Tensor], src: int = 0, group=None) -> None:
+    """Replicate the map: one broadcast per level plane from the owner rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for p in planes:
+        dist.broadcast(p, src=src, group=group)
+
+
+def replicate_map(rep, device, src: int = 0, group=None) -> list[torch.Tensor]:
+    """Broadcast every level's log-odds plane from `src` into this rank's handle and refresh the
+    probability planes of the receivers. Returns the plane views."""
+    planes = [level_plane_tensor(rep, l, device) for l in range(rep.getMapLevels())]
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        broadcast_planes(planes, src, group)
+        torch.cuda.synchronize(device)
+        if dist.get_rank(group) != src:
+            for l in range(rep.getMapLevels()):
+                rep.refresh_level(l, 0)
+            torch.cuda.synchronize(device)
+    return planes
+
+
+def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """all_gather of per-rank row blocks produced by shard_range (uneven blocks are padded)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+
+
+def match_sharded(match_fn, hints, pts, offsets, group=None, device="cpu"):
+    """Match a ragged batch sharded over the ranks of `group`: every rank runs `match_fn(hints,
+    pts, offsets) -> (poses (b,3), cov (b,3,3))` on its contiguous share (no collective on the data
+    path) and the poses / covariances are assembled on every rank."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    h, p, o, (lo, hi) = shard_scans(hints, pts, offsets, rank, world)
+    poses, cov = match_fn(h, p, o)
+    poses_t = torch.as_tensor(np.ascontiguousarray(poses, dtype=np.float32), device=device).reshape(hi - lo, 3)
+    cov_t = torch.as_tensor(np.ascontiguousarray(cov, dtype=np.float32), device=device).reshape(hi - lo, 9)
+    B = hints.shape[0]
+    return gather_rows(poses_t, B, group), gather_rows(cov_t, B, group).reshape(B, 3, 3)

@@ -1,0 +1,102 @@
+"""CPU, world_size 2 on gloo: the multi-process plumbing of hector_slam_b200/parallel.py —
+contiguous scan sharding, map replication by broadcast, result assembly — with the CPU oracle
+standing in for the per-rank matcher (the sharding logic is independent of who computes)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, golden_planes, load_golden
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hector_slam_b200 import parallel
+        from oracle import pyoracle
+
+        g = np.load(os.path.join(ROOT, "tests", "golden", "match3.npz"))
+        size, levels = int(g["size"]), int(g["levels"])
+        # rank 0 owns the map; the others start empty and receive it by broadcast
+        planes = []
+        for l in range(levels):
+            p = np.zeros(((size >> l), (size >> l)), np.float32)
+            if rank == 0:
+                flat = p.reshape(-1)
+                flat[g[f"map_idx{l}"]] = g[f"map_val{l}"]
+            planes.append(torch.from_numpy(p))
+        parallel.broadcast_planes(planes, src=0)
+        orc = pyoracle.Oracle("port", float(g["res"]), size, levels)
+        orc.set_update_factors(0.4, 0.9)
+        for l in range(levels):
+            orc.set_logodds(l, planes[l].numpy())
+
+        K = g["scans"].shape[0]
+        # ragged batch: drop a different number of beams from every scan, one scan empty
+        chunks, offs = [], [0]
+        for k in range(K):
+            s = g["scans"][k][: (0 if k == 5 else 1081 - 13 * k)]
+            chunks.append(s)
+            offs.append(offs[-1] + s.shape[0])
+        pts = np.concatenate(chunks).astype(np.float32)
+        offs = np.asarray(offs, np.int32)
+        hints = g["hints"]
+
+        def match_fn(h, p, o):
+            P, C, _ = orc.match_batch(h, p, o, nthreads=1)
+            return P, C
+
+        poses, cov = parallel.match_sharded(match_fn, hints, pts, offs)
+        # every rank must hold the full, correctly ordered result == the unsharded run
+        want, want_cov, _ = orc.match_batch(hints, pts, offs, nthreads=1)
+        ok = bool(np.array_equal(poses.numpy(), want)) and bool(np.array_equal(cov.numpy(), want_cov))
+        lo, hi = parallel.shard_range(K, rank, world)
+        q.put((rank, ok, (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    from hector_slam_b200 import parallel
+
+    for n in (0, 1, 7, 16, 4096, 65536 + 3):
+        for world in (1, 2, 3, 8):
+            edges = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_ranks_gloo(pyoracle):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in results) == [0, 1]
+    assert all(r[1] for r in results), results
+    assert sorted(r[2] for r in results) == [(0, 8), (8, 16)]
