@@ -51,10 +51,13 @@ def make_workload(seed: int, batch: int):
     world = synth.World.for_map_size(MAP_SIZE)
     rng = np.random.default_rng(1000 + seed)
     poses = world.sample_free_poses(batch, rng)
-    pts, offs = synth.make_scan_batch(world, poses, noise_seed=7 + seed)
+    ranges = synth.make_range_batch(world, poses, noise_seed=7 + seed)
+    pts = np.concatenate([synth.ranges_to_points(ranges[b], 1.0 / RES) for b in range(batch)])
+    offs = (np.arange(batch + 1) * N_PTS).astype(np.int32)
     hints = synth.perturb_hints(poses, seed=1 + seed, dxy=0.1, dpsi=0.05)
     assert pts.shape[0] == batch * N_PTS
-    return world, poses, pts, offs, hints
+    make_workload.ranges = ranges
+    return world, poses, np.ascontiguousarray(pts, dtype=np.float32), offs, hints
 
 
 def build_map_on_gpu(rep, world):
@@ -264,14 +267,15 @@ def main():
         combos = [(w, g, st) for st in (1, 0) for (w, g) in shapes]
         if args.shapes:
             combos = [tuple(int(x) for x in c.split(",")) for c in args.shapes.split(";") if c]
+        combos = [c if len(c) > 3 else tuple(c) + (0,) for c in combos]
         for mode in (("ldg", "tex") if args.gather == "auto" else (args.gather,)):
             r2 = capi.MapRepB200(RES, MAP_SIZE, levels=LEVELS, device=local_rank, update_factor_free=0.4,
                                  update_factor_occupied=0.9, gather_mode={"ldg": 1, "tex": 2}[mode])
             for l in range(LEVELS):
                 r2.upload_level(l, planes_host[l])
-            for (w, g, stage) in combos:
+            for (w, g, stage, unroll) in combos:
                 if True:
-                    r2.set_tuning(warps_per_scan=w, scans_per_block=g, stage_smem=stage)
+                    r2.set_tuning(warps_per_scan=w, scans_per_block=g, stage_smem=stage, unroll=unroll)
                     for i in range(min(3, args.sweep_iters)):
                         r2.match_batch_device(B, d_hints[0].data_ptr(), d_pts[0].data_ptr(), d_offs.data_ptr(), 0, N_PTS,
                                               d_poses.data_ptr(), d_cov.data_ptr(), stream)
@@ -284,7 +288,7 @@ def main():
                     e1.record()
                     torch.cuda.synchronize()
                     ms = e0.elapsed_time(e1) / args.sweep_iters
-                    print(f"sweep mode={mode} stage={stage} W={w} G={g}: {ms:.3f} ms/step  {B / ms * 1e3 / 1e6:.2f} M matches/s",
+                    print(f"sweep mode={mode} stage={stage} W={w} G={g} U={unroll}: {ms:.3f} ms/step  {B / ms * 1e3 / 1e6:.2f} M matches/s",
                           flush=True)
             r2.close()
         return
@@ -322,32 +326,45 @@ def main():
     value = world_size * B * args.steps / (span_ms_max * 1e-3)
     kernel_ms = total_ms / args.steps
 
-    # ---- timed region 2: end to end through hsb_match_batch with pinned host buffers -----------
+    # ---- timed region 2: end to end through the host-buffer C-ABI calls, pinned host memory --------
+    # (a) hsb_match_batch_ranges: raw sensor ranges in (4 B/beam), conversion fused in the kernel
+    # (b) hsb_match_batch:        DataContainer endpoints in (8 B/endpoint), the drop-in format
+    from hector_slam_b200 import synth
+
+    rep.set_scan_format(**synth.SCAN_FORMAT)
+    h_ranges = torch.from_numpy(np.ascontiguousarray(make_workload.ranges)).pin_memory()
     h_pts = torch.from_numpy(pts).pin_memory()
     h_hints = torch.from_numpy(hints).pin_memory()
     h_offs = torch.from_numpy(offs)
     h_poses = torch.empty((B, 3), dtype=torch.float32).pin_memory()
     h_cov = torch.empty((B, 9), dtype=torch.float32).pin_memory()
+    h_poses2 = torch.empty((B, 3), dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        rep.match_batch(h_hints, h_pts, h_offs.numpy(), want_cov=True, out_poses=h_poses, out_cov=h_cov)
+        rep.match_batch_ranges(h_hints, h_ranges, want_cov=True, out_poses=h_poses, out_cov=h_cov)
 
-    for _ in range(max(3, args.warmup)):
-        step_e2e()
-    torch.cuda.synchronize()
-    if world_size > 1:
-        dist.barrier()
-    launches_e0 = rep.launch_count
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    e2e_launches = rep.launch_count - launches_e0
-    te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world_size * B * args.steps / float(te.item())
+    def step_e2e_xy():
+        rep.match_batch(h_hints, h_pts, h_offs.numpy(), want_cov=True, out_poses=h_poses2, out_cov=h_cov)
+
+    def time_host(fn):
+        for _ in range(max(3, args.warmup)):
+            fn()
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        l0 = rep.launch_count
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world_size * B * args.steps / float(te.item()), rep.launch_count - l0
+
+    e2e_xy_value, _ = time_host(step_e2e_xy)
+    e2e_value, e2e_launches = time_host(step_e2e)
     clocks = sampler.stop() if rank == 0 else None
 
     # parity spot check of the e2e result against the device-resident path (same inputs)
@@ -370,9 +387,15 @@ def main():
                                 f"({nbuf * pts.nbytes / 1e6:.0f} MB of endpoints); the frozen map is reused by design",
                        "map_replication": "rank 0 builds, one NCCL broadcast" if world_size > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "scan-matches/s",
-                    "h2d_bytes_per_step": int(pts.nbytes + hints.nbytes + offs.nbytes),
+                    "h2d_bytes_per_step": int(make_workload.ranges.nbytes + hints.nbytes),
                     "d2h_bytes_per_step": int(B * 12 + B * 36), "launches": int(e2e_launches),
+                    "call": "hsb_match_batch_ranges: pinned host sensor ranges (4 B/beam) + hints in, poses + "
+                            "covariances out; scan->endpoint conversion fused into the match kernel",
                     "max_abs_diff_vs_device_path": same},
+            "e2e_endpoints": {"value": e2e_xy_value, "unit": "scan-matches/s",
+                              "h2d_bytes_per_step": int(pts.nbytes + hints.nbytes + offs.nbytes),
+                              "d2h_bytes_per_step": int(B * 12 + B * 36),
+                              "call": "hsb_match_batch: DataContainer endpoints (8 B each) in"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "hsb::match_kernel",

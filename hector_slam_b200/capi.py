@@ -25,7 +25,8 @@ EXPORTED = [
     "hsb_hessian_derivs", "hsb_update_by_scan", "hsb_update_level_by_scan", "hsb_on_map_updated",
     "hsb_upload_level", "hsb_download_level", "hsb_download_prob", "hsb_level_logodds_device_ptr",
     "hsb_refresh_level", "hsb_last_error", "hsb_status_string", "hsb_get_launch_count", "hsb_get_gather_mode",
-    "hsb_set_tuning", "hsb_version",
+    "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
+    "hsb_match_batch_ranges_device",
 ]
 
 
@@ -44,6 +45,11 @@ class HsbConfig(C.Structure):
         ("gather_mode", C.c_int),
         ("reserved", C.c_int * 7),
     ]
+
+
+class HsbScanFormat(C.Structure):
+    _fields_ = [("n_beams", C.c_int), ("angle_min", C.c_float), ("angle_increment", C.c_float),
+                ("range_min", C.c_float), ("range_max", C.c_float)]
 
 
 class HsbError(RuntimeError):
@@ -101,6 +107,10 @@ def load_library() -> C.CDLL:
     sig("hsb_get_gather_mode", i, vp)
     sig("hsb_set_tuning", i, vp, C.c_char_p, i)
     sig("hsb_version", C.c_char_p)
+    sig("hsb_set_scan_format", i, vp, C.POINTER(HsbScanFormat))
+    sig("hsb_scan_to_points", i, vp, vp, vp, ip)
+    sig("hsb_match_batch_ranges", i, vp, i, vp, vp, vp, vp)
+    sig("hsb_match_batch_ranges_device", i, vp, i, vp, vp, vp, vp, vp)
     _lib = L
     return L
 
@@ -281,6 +291,44 @@ class MapRepB200:
         """Raw device pointers (ints, e.g. tensor.data_ptr()) and a CUDA stream handle; asynchronous."""
         self._check(self.lib.hsb_match_batch_device(self.h, int(B), d_hints, d_points, d_offsets, int(n_shared),
                                                     int(max_points_per_scan), d_out_poses, d_out_cov, stream))
+
+    # -- raw ranges in (rosLaserScanToDataContainer fused into the match kernel) -----------------
+    def set_scan_format(self, n_beams: int, angle_min: float, angle_increment: float, range_min: float,
+                        range_max: float):
+        fmt = HsbScanFormat(int(n_beams), float(angle_min), float(angle_increment), float(range_min), float(range_max))
+        self._check(self.lib.hsb_set_scan_format(self.h, C.byref(fmt)))
+        self.n_beams = int(n_beams)
+
+    def scan_to_points(self, ranges) -> np.ndarray:
+        r = _f32(ranges).reshape(-1)
+        assert r.size == self.n_beams
+        out = np.zeros((self.n_beams, 2), np.float32)
+        n = C.c_int()
+        self._check(self.lib.hsb_scan_to_points(self.h, r.ctypes.data, out.ctypes.data, C.byref(n)))
+        return out[: n.value].copy()
+
+    def match_batch_ranges(self, hints, ranges, want_cov: bool = True, out_poses=None, out_cov=None):
+        """ranges: (B, n_beams) float32 host array / pinned tensor."""
+        B = int(hints.shape[0])
+        if isinstance(hints, np.ndarray):
+            hints = _f32(hints).reshape(-1, 3)
+        if isinstance(ranges, np.ndarray):
+            ranges = _f32(ranges).reshape(B, self.n_beams)
+        if out_poses is None:
+            out_poses = np.zeros((B, 3), np.float32)
+        if want_cov and out_cov is None:
+            out_cov = np.zeros((B, 9), np.float32)
+        self._check(self.lib.hsb_match_batch_ranges(self.h, B, _ptr(hints), _ptr(ranges), _ptr(out_poses),
+                                                    _ptr(out_cov) if want_cov else None))
+        cov = None
+        if want_cov:
+            cov = out_cov.reshape(B, 3, 3) if isinstance(out_cov, np.ndarray) else out_cov
+        return out_poses, cov
+
+    def match_batch_ranges_device(self, B: int, d_hints: int, d_ranges: int, d_out_poses: int, d_out_cov: int | None,
+                                  stream: int = 0):
+        self._check(self.lib.hsb_match_batch_ranges_device(self.h, int(B), d_hints, d_ranges, d_out_poses, d_out_cov,
+                                                           stream))
 
     # -- planes ----------------------------------------------------------------------------------
     def upload_level(self, level: int, logodds):

@@ -53,12 +53,16 @@ struct hsb_handle {
   DevBuf d_hints, d_pts, d_offsets, d_poses, d_cov, d_scratch;
   // "containers of the last match" (MapRepMultiMap::dataContainers) and the update scan
   DevBuf d_last_pts, d_upd_pts;
+  // raw-range input (N2)
+  DevBuf d_beam_cs, d_ranges;
+  hsb_scan_format fmt = hsb_scan_format();
+  bool fmt_set = false;
   int last_n = 0;
   float last_origo[2] = {0.f, 0.f};
   // pinned host scratch
   float* h_pin = nullptr;  // 64 floats
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0;
   uint64_t launches = 0;
   std::string err;
 };
@@ -179,17 +183,18 @@ void fill_level_dev(const hsb_handle* h, int l, HsbLevelDev& d) {
 }
 
 // ---- match launch -----------------------------------------------------------------------------
-template <int W, int G, int MODE>
+template <int W, int G, int MODE, int U>
 int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   size_t header = hsb::MatchSmem<W, G>::kHeaderBytes;
   int cap = 0;
-  if (h->tune_stage_smem) {
+  if (h->tune_stage_smem || P.ranges) {
     cap = ((max_n + 1) + 1) & ~1;  // n + head padding, even
     if (header + (size_t)G * cap * 8 > 200 * 1024) cap = 0;
   }
+  if (P.ranges && cap == 0) return fail(h, HSB_ERR_UNSUPPORTED, "scan too long for the fused range conversion (%d beams)", max_n);
   P.pts_cap = cap;
   size_t smem = header + (size_t)G * cap * 8;
-  auto kern = hsb::match_kernel<W, G, MODE>;
+  auto kern = hsb::match_kernel<W, G, MODE, U>;
   if (smem > 48 * 1024) {
     HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -225,38 +230,58 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
 }
 
 template <int MODE>
-int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int W, int G) {
-#define HSB_CASE(w, g) \
-  if (W == w && G == g) return launch_match_t<w, g, MODE>(h, P, max_n, st)
-  HSB_CASE(1, 1);
-  HSB_CASE(1, 2);
-  HSB_CASE(1, 4);
-  HSB_CASE(1, 8);
-  HSB_CASE(2, 1);
-  HSB_CASE(2, 2);
-  HSB_CASE(2, 4);
-  HSB_CASE(4, 1);
-  HSB_CASE(4, 2);
-  HSB_CASE(8, 1);
-  HSB_CASE(16, 1);
-  HSB_CASE(17, 1);
-  HSB_CASE(32, 1);
+int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int W, int G, int U) {
+#define HSB_CASE(w, g, u) \
+  if (W == w && G == g && U == u) return launch_match_t<w, g, MODE, u>(h, P, max_n, st)
+  HSB_CASE(1, 1, 4);
+  HSB_CASE(1, 2, 4);
+  HSB_CASE(1, 4, 4);
+  HSB_CASE(1, 8, 4);
+  HSB_CASE(2, 1, 4);
+  HSB_CASE(2, 2, 4);
+  HSB_CASE(2, 4, 4);
+  HSB_CASE(4, 1, 4);
+  HSB_CASE(4, 2, 4);
+  HSB_CASE(8, 1, 4);
+  HSB_CASE(16, 1, 4);
+  HSB_CASE(17, 1, 4);
+  HSB_CASE(32, 1, 4);
+  // deeper gather batches: the whole per-lane share of a 1081-point scan in flight at once
+  HSB_CASE(1, 1, 8);
+  HSB_CASE(2, 1, 8);
+  HSB_CASE(4, 1, 8);
+  HSB_CASE(4, 1, 9);
+  HSB_CASE(8, 1, 5);
+  HSB_CASE(16, 1, 3);
 #undef HSB_CASE
-  return fail(h, HSB_ERR_INVALID_ARG, "unsupported tuning warps_per_scan=%d scans_per_block=%d", W, G);
+  return fail(h, HSB_ERR_INVALID_ARG, "unsupported tuning warps_per_scan=%d scans_per_block=%d unroll=%d", W, G, U);
 }
 
 int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   int W = h->tune_warps_per_scan, G = h->tune_scans_per_block;
   if (W <= 0) {
-    // about 32 resident warps per SM: one warp per scan for big batches, a whole CTA for one scan
-    long want = ((long)h->sm_count * 32 + P.B - 1) / P.B;
+    // Measured on B200 (profiles/r01_sweep_batches.log): one or two warps per scan once the batch
+    // fills the chip, more warps per scan for small batches, never more than 8 (the per-evaluation
+    // reduction / barrier cost grows with the group size).
+    long want = ((long)h->sm_count * 24) / (P.B > 0 ? P.B : 1);
     W = 1;
-    while (W < want && W < 32) W *= 2;
-    if (W == 32 && max_n <= 17 * 64 && max_n > 1024) W = 17;  // 1081-pt scan: exactly 2 points per lane
+    while (W * 2 <= want && W < 8) W *= 2;
+    if (P.B >= 3072) W = 2;
   }
   if (G <= 0) G = 1;
-  if (h->gather_mode == HSB_GATHER_TEX) return launch_match_mode<hsb::MODE_TEX>(h, P, max_n, st, W, G);
-  return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G);
+  int U = h->tune_unroll > 0 ? h->tune_unroll : 4;
+  if (h->tune_unroll <= 0 && h->tune_warps_per_scan <= 0 && W == 8 && G == 1 && max_n <= 5 * 256) U = 5;  // one gather round
+  if (h->gather_mode == HSB_GATHER_TEX) return launch_match_mode<hsb::MODE_TEX>(h, P, max_n, st, W, G, U);
+  return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G, U);
+}
+
+// Copy/compute pipeline granularity of the host-buffer batch calls.  Chunks must stay large enough
+// for the match kernel to run at full efficiency (>= 1024 scans, profiles/r01_sweep_batches.log) and
+// few enough that the un-overlapped tail (last chunk's kernel) stays small: 4 chunks.
+int pipeline_chunk(int B) {
+  int c = (B + 3) / 4;
+  if (c < 1024) c = 1024;
+  return c < B ? c : B;
 }
 
 void fill_match_params(const hsb_handle* h, HsbMatchParams& P) {
@@ -426,7 +451,8 @@ int hsb_destroy(hsb_handle* h) {
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (int l = 0; l < HSB_MAX_LEVELS; ++l) destroy_level(h, h->lv[l]);
-  DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_last_pts, &h->d_upd_pts};
+  DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_last_pts, &h->d_upd_pts,
+                    &h->d_beam_cs, &h->d_ranges};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -473,6 +499,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "scans_per_block")) h->tune_scans_per_block = value;
   else if (!strcmp(key, "stage_smem")) h->tune_stage_smem = value;
   else if (!strcmp(key, "chunk")) h->tune_chunk = value;
+  else if (!strcmp(key, "unroll")) h->tune_unroll = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }
@@ -583,7 +610,7 @@ int hsb_match_batch(hsb_handle* h, int B, const float* hints, const float* pts, 
 
   // Pipeline: the batch is cut into chunks; chunk c's host->device copy runs on copy stream c%2
   // while chunk c-1 is being matched, and results stream back behind each kernel.
-  int chunk = h->tune_chunk > 0 ? h->tune_chunk : (B >= 2048 ? (B + 3) / 4 : B);
+  int chunk = h->tune_chunk > 0 ? h->tune_chunk : pipeline_chunk(B);
   if (!offsets) chunk = B;  // shared scan: nothing big to overlap
   cudaStream_t s0 = h->copy_stream[0];
   if (offsets) {
@@ -641,6 +668,121 @@ int hsb_hessian_derivs(hsb_handle* h, int level, const float pose_map[3], const 
   HSB_CUDA(h, cudaStreamSynchronize(st));
   memcpy(H_out, h->h_pin + 32, 9 * sizeof(float));
   memcpy(dTr_out, h->h_pin + 41, 3 * sizeof(float));
+  return HSB_OK;
+}
+
+// ---- raw ranges (N2) ---------------------------------------------------------------------------
+
+int hsb_set_scan_format(hsb_handle* h, const hsb_scan_format* fmt) {
+  if (!h || !fmt || fmt->n_beams < 1 || fmt->n_beams > (1 << 20)) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int s = ensure(h, h->d_beam_cs, (size_t)fmt->n_beams * 8);
+  if (s != HSB_OK) return s;
+  std::vector<float> tab((size_t)fmt->n_beams * 2);
+  float angle = fmt->angle_min;  // HectorMappingRos.cpp:487
+  for (int i = 0; i < fmt->n_beams; ++i) {
+    tab[2 * (size_t)i] = cosf(angle);      // :501 cos(angle) on a float
+    tab[2 * (size_t)i + 1] = sinf(angle);  // :502
+    volatile float next = angle + fmt->angle_increment;  // :505, fp32 accumulation
+    angle = next;
+  }
+  HSB_CUDA(h, cudaMemcpy(h->d_beam_cs.p, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->fmt = *fmt;
+  h->fmt_set = true;
+  return HSB_OK;
+}
+
+static void fill_range_params(const hsb_handle* h, HsbMatchParams& P, const float* d_ranges) {
+  P.ranges = d_ranges;
+  P.beam_cs = static_cast<const float2*>(h->d_beam_cs.p);
+  P.n_beams = h->fmt.n_beams;
+  P.range_min = h->fmt.range_min;
+  volatile float mx = h->fmt.range_max - 0.1f;  // :493 maxRangeForContainer
+  P.range_max_c = mx;
+  P.scale_to_map = h->lv[0].scale;
+}
+
+int hsb_scan_to_points(hsb_handle* h, const float* ranges, float* out_xy, int* out_n) {
+  if (!h || !ranges || !out_xy || !out_n) return HSB_ERR_INVALID_ARG;
+  if (!h->fmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_scan_format has not been called");
+  DeviceGuard guard(h->device);
+  const int nb = h->fmt.n_beams;
+  int s;
+  if ((s = ensure(h, h->d_ranges, (size_t)nb * 4)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_pts, (size_t)nb * 8 + 16)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_scratch, 64 * sizeof(float))) != HSB_OK) return s;
+  cudaStream_t st = h->stream;
+  HSB_CUDA(h, cudaMemcpyAsync(h->d_ranges.p, ranges, (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+  HsbMatchParams P;
+  memset(&P, 0, sizeof(P));
+  fill_range_params(h, P, static_cast<const float*>(h->d_ranges.p));
+  int* d_n = reinterpret_cast<int*>(static_cast<float*>(h->d_scratch.p) + 48);
+  hsb::scan_to_points_kernel<<<1, 256, 0, st>>>(P.ranges, P.beam_cs, nb, P.range_min, P.range_max_c, P.scale_to_map,
+                                                static_cast<float2*>(h->d_pts.p), d_n);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 48, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  int n = *reinterpret_cast<int*>(h->h_pin + 48);
+  if (n > 0) HSB_CUDA(h, cudaMemcpy(out_xy, h->d_pts.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  *out_n = n;
+  return HSB_OK;
+}
+
+int hsb_match_batch_ranges_device(hsb_handle* h, int B, const float* d_hints, const float* d_ranges, float* d_out_poses,
+                                  float* d_out_cov, void* stream) {
+  if (!h || B < 0 || !d_hints || !d_ranges || !d_out_poses) return HSB_ERR_INVALID_ARG;
+  if (!h->fmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_scan_format has not been called");
+  if (B == 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  HsbMatchParams P;
+  fill_match_params(h, P);
+  P.B = B;
+  P.hints = d_hints;
+  P.out_poses = d_out_poses;
+  P.out_cov = d_out_cov;
+  fill_range_params(h, P, d_ranges);
+  return launch_match(h, P, h->fmt.n_beams, (cudaStream_t)stream);
+}
+
+int hsb_match_batch_ranges(hsb_handle* h, int B, const float* hints, const float* ranges, float* out_poses, float* out_cov) {
+  if (!h || B < 0 || !hints || !ranges || !out_poses) return HSB_ERR_INVALID_ARG;
+  if (!h->fmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_scan_format has not been called");
+  if (B == 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  const size_t nb = (size_t)h->fmt.n_beams;
+  int s;
+  if ((s = ensure(h, h->d_hints, (size_t)B * 12)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_ranges, (size_t)B * nb * 4)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_poses, (size_t)B * 12)) != HSB_OK) return s;
+  if (out_cov && (s = ensure(h, h->d_cov, (size_t)B * 36)) != HSB_OK) return s;
+  float* d_hints = static_cast<float*>(h->d_hints.p);
+  float* d_ranges = static_cast<float*>(h->d_ranges.p);
+  float* d_poses = static_cast<float*>(h->d_poses.p);
+  float* d_cov = out_cov ? static_cast<float*>(h->d_cov.p) : nullptr;
+  // same copy/compute pipeline as hsb_match_batch
+  int chunk = h->tune_chunk > 0 ? h->tune_chunk : pipeline_chunk(B);
+  cudaStream_t s0 = h->copy_stream[0];
+  HSB_CUDA(h, cudaMemcpyAsync(d_hints, hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
+  HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
+  HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
+  int ci = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
+    int b1 = b0 + chunk < B ? b0 + chunk : B;
+    cudaStream_t st = h->copy_stream[ci & 1];
+    HSB_CUDA(h, cudaMemcpyAsync(d_ranges + (size_t)b0 * nb, ranges + (size_t)b0 * nb, (size_t)(b1 - b0) * nb * 4,
+                                cudaMemcpyHostToDevice, st));
+    s = hsb_match_batch_ranges_device(h, b1 - b0, d_hints + 3 * (size_t)b0, d_ranges + (size_t)b0 * nb,
+                                      d_poses + 3 * (size_t)b0, d_cov ? d_cov + 9 * (size_t)b0 : nullptr, st);
+    if (s != HSB_OK) return s;
+    HSB_CUDA(h, cudaMemcpyAsync(out_poses + 3 * (size_t)b0, d_poses + 3 * (size_t)b0, (size_t)(b1 - b0) * 12,
+                                cudaMemcpyDeviceToHost, st));
+    if (out_cov)
+      HSB_CUDA(h, cudaMemcpyAsync(out_cov + 9 * (size_t)b0, d_cov + 9 * (size_t)b0, (size_t)(b1 - b0) * 36,
+                                  cudaMemcpyDeviceToHost, st));
+  }
+  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[0]));
+  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[1]));
   return HSB_OK;
 }
 

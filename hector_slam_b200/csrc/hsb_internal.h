@@ -32,6 +32,14 @@ struct HsbMatchParams {
   float* out_poses;     // B x 3
   float* out_cov;       // B x 9 or nullptr
   int pts_cap;          // points of smem staging per scan group (0 = read points from global)
+  // raw-range input (N2: rosLaserScanToDataContainer fused into the staging step); ranges == nullptr
+  // selects the endpoint input above
+  const float* ranges;      // B x n_beams
+  const float2* beam_cs;    // n_beams x (cos, sin) of the accumulated beam angle
+  int n_beams;
+  float range_min, range_max_c;  // keep range_min < r < range_max - 0.1
+  float scale_to_map;
+  int* cnt_scratch;         // unused (reserved)
 };
 
 struct HsbUpdateLevelDev {

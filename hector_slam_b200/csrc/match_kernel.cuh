@@ -38,12 +38,51 @@ __device__ __forceinline__ void affine_apply_exact(const float* m, float vx, flo
   oy = __fadd_rn(__fmul_rn(m[3], vx), __fadd_rn(__fmul_rn(m[4], vy), m[5]));
 }
 
-// util::normalize_angle, UtilFunctions.h:37-49 (double arithmetic because M_PI is a double).
+// util::normalize_angle, UtilFunctions.h:37-49:  a = fmod(fmod(angle, 2pi) + 2pi, 2pi); if (a > pi) a -= 2pi,
+// in double because M_PI is a double, narrowed to float where the reference narrows.  Both fmods are
+// exact operations; for |angle| < 2pi the first is the identity and the second is one exact
+// subtraction (Sterbenz), so the common case needs no fmod at all — bit-identical either way.
 __device__ __forceinline__ float normalize_angle(float angle) {
   const double two_pi = 2.0 * 3.14159265358979323846;
-  float a = (float)fmod(fmod((double)angle, two_pi) + two_pi, two_pi);
+  double r = (double)angle;
+  if (!(fabs(r) < two_pi)) r = fmod(r, two_pi);
+  r += two_pi;                       // in (0, 4pi)
+  if (r >= two_pi) r -= two_pi;      // == fmod(r, two_pi), exact
+  float a = (float)r;
   if ((double)a > 3.14159265358979323846) a = (float)((double)a - two_pi);
   return a;
+}
+
+// sin/cos of the pose angle.  The reference calls sinf/cosf (OccGridMapUtil.h:70-71, :351); a
+// correctly rounded float result is reproduced by evaluating in double and rounding once.  Between
+// two evaluations the angle moves by at most the 0.2 rad clamp, so instead of a full double sincos
+// per evaluation (range reduction + two polynomials + slow path) the pair is ROTATED by the exact
+// difference d = psi_new - psi_old with 12th-order Taylor polynomials (|d| <= 0.25: truncation
+// < 3e-19, accumulated error over a level < 1e-15, i.e. ~1e-8 of a float ulp).
+__device__ __forceinline__ void sincos_advance(float psi_old, float psi_new, double& s, double& c) {
+  const double d = (double)psi_new - (double)psi_old;  // exact in double
+  if (!(fabs(d) <= 0.25)) {
+    sincos((double)psi_new, &s, &c);
+    return;
+  }
+  const double d2 = d * d;
+  double sn = -1.0 / 39916800.0;
+  sn = fma(sn, d2, 1.0 / 362880.0);
+  sn = fma(sn, d2, -1.0 / 5040.0);
+  sn = fma(sn, d2, 1.0 / 120.0);
+  sn = fma(sn, d2, -1.0 / 6.0);
+  sn = fma(sn * d2, d, d);
+  double cn = 1.0 / 479001600.0;
+  cn = fma(cn, d2, -1.0 / 3628800.0);
+  cn = fma(cn, d2, 1.0 / 40320.0);
+  cn = fma(cn, d2, -1.0 / 720.0);
+  cn = fma(cn, d2, 1.0 / 24.0);
+  cn = fma(cn, d2, -0.5);
+  cn = fma(cn, d2, 1.0);
+  const double c2 = fma(c, cn, -(s * sn));
+  const double s2 = fma(s, cn, c * sn);
+  c = c2;
+  s = s2;
 }
 
 // Eigen's fixed-size 3x3 inverse times vector (ScanMatcher.h:205 `H.inverse() * dTr`): cyclic
@@ -321,19 +360,71 @@ __device__ __forceinline__ void group_sync(int g) {
   }
 }
 
-// Shared-memory carve-up for G groups: [G] mbarriers | [G][2][W][12] reduction slots | points
+// ---- N2: sensor_msgs/LaserScan ranges -> DataContainer endpoints, fused into the staging step ----
+// Restates HectorMappingRos::rosLaserScanToDataContainer (hector_mapping/src/HectorMappingRos.cpp:
+// 483-507): keep returns with range_min < r < range_max - 0.1 (:493,499), dist = r * scaleToMap,
+// endpoint = (cos(angle) * dist, sin(angle) * dist) (:501-502); the beam angle is accumulated in
+// fp32 on the host (`angle += angle_increment`, :505) and arrives as a (cos, sin) table.  Valid
+// endpoints are compacted IN BEAM ORDER into `dst` (the container's order); returns their number.
+// Warp w converts the contiguous beam range [w*chunk, (w+1)*chunk).
+template <int W>
+__device__ __forceinline__ int stage_from_ranges(const float* __restrict__ r_scan, const float2* __restrict__ beam_cs,
+                                                 int n_beams, float rmin, float rmaxc, float scale, float2* dst,
+                                                 int* warp_cnt, int g, int w, int lane) {
+  const int chunk = (n_beams + W - 1) / W;
+  const int b0 = w * chunk, b1 = min(n_beams, b0 + chunk);
+  int mine = 0;
+  if (W > 1) {
+    for (int base = b0; base < b1; base += 32) {
+      const int i = base + lane;
+      const float r = i < b1 ? __ldg(r_scan + i) : 0.0f;
+      const bool v = (i < b1) && (r > rmin) && (r < rmaxc);
+      mine += __popc(__ballot_sync(0xffffffffu, v));
+    }
+    if (lane == 0) warp_cnt[w] = mine;
+    group_sync<W>(g);
+  }
+  int off = 0, total = 0;
+  if (W > 1) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const int c = warp_cnt[k];
+      if (k < w) off += c;
+      total += c;
+    }
+  }
+  for (int base = b0; base < b1; base += 32) {
+    const int i = base + lane;
+    const float r = i < b1 ? __ldg(r_scan + i) : 0.0f;
+    const bool v = (i < b1) && (r > rmin) && (r < rmaxc);
+    const unsigned m = __ballot_sync(0xffffffffu, v);
+    if (v) {
+      const float dist = __fmul_rn(r, scale);
+      const float2 cs = __ldg(beam_cs + i);
+      dst[off + __popc(m & ((1u << lane) - 1u))] = make_float2(__fmul_rn(cs.x, dist), __fmul_rn(cs.y, dist));
+    }
+    off += __popc(m);
+  }
+  if (W == 1) total = off;
+  group_sync<W>(g);  // endpoints visible to the whole group (also protects warp_cnt for the next scan)
+  return total;
+}
+
+// Shared-memory carve-up for G groups: [G] mbarriers | [G][2][9][32] reduction slots | points
 template <int W, int G>
 struct MatchSmem {
-  static constexpr int kRedFloats = (W > 1) ? G * 2 * W * 12 : 0;
-  static constexpr int kHeaderBytes = ((G * 8 + kRedFloats * 4) + 15) / 16 * 16;
+  static constexpr int kRedFloats = (W > 1) ? G * 2 * 9 * 32 : 0;
+  static constexpr int kCntInts = G * 32;
+  static constexpr int kHeaderBytes = ((G * 8 + kRedFloats * 4 + kCntInts * 4) + 15) / 16 * 16;
 };
 
-template <int W, int G, int MODE>
+template <int W, int G, int MODE, int U>
 __global__ void __launch_bounds__(W * G * 32)
     match_kernel(const __grid_constant__ HsbMatchParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* mbars = reinterpret_cast<uint64_t*>(smem_raw);
   float* red_all = reinterpret_cast<float*>(smem_raw + G * 8);
+  int* cnt_all = reinterpret_cast<int*>(smem_raw + G * 8 + MatchSmem<W, G>::kRedFloats * 4);
   float2* spts_all = reinterpret_cast<float2*>(smem_raw + MatchSmem<W, G>::kHeaderBytes);
 
   constexpr int GT = W * 32;  // threads per group
@@ -343,8 +434,9 @@ __global__ void __launch_bounds__(W * G * 32)
   const int lane = t & 31;
   const int cap = P.pts_cap;
   float2* spts = spts_all + (size_t)g * cap;
-  float* red = red_all + g * (2 * W * 12);
+  float* red = red_all + g * (2 * 9 * 32);
   uint64_t* mbar = mbars + g;
+  int* warp_cnt = cnt_all + g * 32;
 
   if (t == 0) mbar_init(mbar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -364,7 +456,12 @@ __global__ void __launch_bounds__(W * G * 32)
     const float2* __restrict__ gpts = P.pts + beg;
     const float2* spts_scan = spts;  // shared-memory copy of the scan (valid when staged)
     bool staged = false;
-    if (cap > 0 && n < cap && n > 0) {
+    if (P.ranges) {
+      // raw ranges in: convert + compact straight into shared memory (host guarantees cap >= n_beams)
+      n = stage_from_ranges<W>(P.ranges + (size_t)scan * P.n_beams, P.beam_cs, P.n_beams, P.range_min, P.range_max_c,
+                               P.scale_to_map, spts, warp_cnt, g, w, lane);
+      staged = true;
+    } else if (cap > 0 && n < cap && n > 0) {
       // Stage the scan into shared memory.  Point i goes to spts[i + head] where head = 1 iff the
       // scan starts on an odd point (8- but not 16-byte aligned), so that global and shared
       // addresses share their 16-byte phase and the even-aligned body can move as ONE bulk copy;
@@ -399,32 +496,41 @@ __global__ void __launch_bounds__(W * G * 32)
         const LevelRegs LR = level_regs(L);
         float ex, ey, epsi = wpsi;
         affine_apply_exact(L.mtw, wx, wy, ex, ey);  // ScanMatcher.h:70 getMapCoordsPose
+        double sd, cd;
+        sincos((double)epsi, &sd, &cd);              // OccGridMapUtil.h:70-71 (sinf/cosf, correctly rounded)
         for (int e = 0; e < L.evals; ++e) {          // ScanMatcher.h:74 + :94-97
-          double sd, cd;
-          sincos((double)epsi, &sd, &cd);            // OccGridMapUtil.h:70-71 (sinf/cosf, correctly rounded)
           const float cs = (float)cd * L.pt_scale, ss = (float)sd * L.pt_scale;
           Acc a;
           acc_zero(a);
           if (staged)
-            eval_points<MODE, HSB_UNROLL>(LR, spts_scan, t, GT, n, cs, ss, ex, ey, a);
+            eval_points<MODE, U>(LR, spts_scan, t, GT, n, cs, ss, ex, ey, a);
           else
-            eval_points<MODE, HSB_UNROLL>(LR, gpts, t, GT, n, cs, ss, ex, ey, a);
+            eval_points<MODE, U>(LR, gpts, t, GT, n, cs, ss, ex, ey, a);
           warp_reduce(a);
           if (W > 1) {
-            float* slot = red + (red_flip * W + w) * 12;
+            // second stage: the W per-warp sums of each of the 9 values sit transposed in shared
+            // memory ([value][warp]); lane l picks warp (l mod WP) and a log2(WP)-step butterfly
+            // leaves the group totals in every lane of every warp (same order everywhere)
+            constexpr int WP = W <= 2 ? 2 : W <= 4 ? 4 : W <= 8 ? 8 : W <= 16 ? 16 : 32;
+            float* buf = red + red_flip * (9 * 32);
             if (lane == 0) {
-              slot[0] = a.h00; slot[1] = a.h11; slot[2] = a.h22; slot[3] = a.h01; slot[4] = a.h02;
-              slot[5] = a.h12; slot[6] = a.d0;  slot[7] = a.d1;  slot[8] = a.d2;
+              buf[0 * 32 + w] = a.h00; buf[1 * 32 + w] = a.h11; buf[2 * 32 + w] = a.h22;
+              buf[3 * 32 + w] = a.h01; buf[4 * 32 + w] = a.h02; buf[5 * 32 + w] = a.h12;
+              buf[6 * 32 + w] = a.d0;  buf[7 * 32 + w] = a.d1;  buf[8 * 32 + w] = a.d2;
             }
             group_sync<W>(g);
-            const float* base = red + red_flip * W * 12;
-            acc_zero(a);
+            const int src = lane & (WP - 1);
+            const bool have = src < W;
+            float v[9];
 #pragma unroll
-            for (int k = 0; k < W; ++k) {
-              const float* s = base + k * 12;
-              a.h00 += s[0]; a.h11 += s[1]; a.h22 += s[2]; a.h01 += s[3]; a.h02 += s[4];
-              a.h12 += s[5]; a.d0 += s[6];  a.d1 += s[7];  a.d2 += s[8];
+            for (int k = 0; k < 9; ++k) v[k] = have ? buf[k * 32 + src] : 0.0f;
+#pragma unroll
+            for (int o = WP / 2; o > 0; o >>= 1) {
+#pragma unroll
+              for (int k = 0; k < 9; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
             }
+            a.h00 = v[0]; a.h11 = v[1]; a.h22 = v[2]; a.h01 = v[3]; a.h02 = v[4];
+            a.h12 = v[5]; a.d0 = v[6];  a.d1 = v[7];  a.d2 = v[8];
             red_flip ^= 1;
           }
           last = a;
@@ -435,7 +541,9 @@ __global__ void __launch_bounds__(W * G * 32)
             else if (d2 < -0.2f) d2 = -0.2f;
             ex = __fadd_rn(ex, d0);              // :217
             ey = __fadd_rn(ey, d1);
-            epsi = __fadd_rn(epsi, d2);
+            const float npsi = __fadd_rn(epsi, d2);
+            if (e + 1 < L.evals) sincos_advance(epsi, npsi, sd, cd);
+            epsi = npsi;
           }
         }
         epsi = normalize_angle(epsi);                 // ScanMatcher.h:170
@@ -458,6 +566,16 @@ __global__ void __launch_bounds__(W * G * 32)
     }
     if (cap > 0) group_sync<W>(g);  // everyone done with spts before the next bulk copy lands
   }
+}
+
+// The conversion alone (one scan, one CTA of 8 warps), for the N2 parity tests.
+__global__ void __launch_bounds__(256)
+    scan_to_points_kernel(const float* __restrict__ ranges, const float2* __restrict__ beam_cs, int n_beams, float rmin,
+                          float rmaxc, float scale, float2* __restrict__ out, int* __restrict__ out_n) {
+  __shared__ int warp_cnt[32];
+  const int n = stage_from_ranges<8>(ranges, beam_cs, n_beams, rmin, rmaxc, scale, out, warp_cnt, 0, threadIdx.x >> 5,
+                                     threadIdx.x & 31);
+  if (threadIdx.x == 0) *out_n = n;
 }
 
 // Single evaluation (the getCompleteHessianDerivs seam): one CTA of 256 threads.

@@ -179,6 +179,23 @@ def make_scan(world: World, pose, rng: np.random.Generator | None, scale_to_map:
     return ranges_to_points(r, scale_to_map)
 
 
+def make_range_batch(world: World, poses: np.ndarray, noise_seed: int = 7, sigma: float = 0.01) -> np.ndarray:
+    """Raw ranges (B, 1081) float32 — what sensor_msgs/LaserScan carries — same noise stream as
+    make_scan_batch, so ranges_to_points(make_range_batch(..)[b]) == make_scan_batch(..) scan b."""
+    rng = np.random.default_rng(noise_seed)
+    out = np.empty((len(poses), N_BEAMS), dtype=np.float32)
+    for b, p in enumerate(poses):
+        r = world.cast(p)
+        if sigma > 0:
+            r = r + rng.normal(0.0, sigma, r.shape)
+        out[b] = r.astype(np.float32)
+    return out
+
+
+SCAN_FORMAT = dict(n_beams=N_BEAMS, angle_min=float(ANGLE_MIN), angle_increment=float(ANGLE_INC),
+                   range_min=float(RANGE_MIN), range_max=float(RANGE_MAX))
+
+
 def make_scan_batch(world: World, poses: np.ndarray, noise_seed: int = 7, scale_to_map: float = 20.0,
                     sigma: float = 0.01):
     """Scans for every pose. Returns (pts (sum_n, 2) f32, offsets (B+1,) i32)."""

@@ -130,6 +130,30 @@ int hsb_match_batch_device(hsb_handle* h, int B, const float* d_hints_world, con
                            const int* d_offsets, int n_shared, int max_points_per_scan, float* d_out_poses_world,
                            float* d_out_cov, void* stream);
 
+/* ---- raw laser ranges in (the step before the path: scan -> DataContainer) ---------------------*/
+/* The sensor_msgs/LaserScan fields HectorMappingRos::rosLaserScanToDataContainer reads
+ * (hector_mapping/src/HectorMappingRos.cpp:483-507).  Setting a format builds the per-beam
+ * (cos, sin) table on the host exactly as the node does (fp32 `angle += angle_increment`, cos/sin of
+ * the float angle) and keeps it on the device. */
+typedef struct hsb_scan_format {
+  int   n_beams;          /* ranges.size()                                   */
+  float angle_min;        /* scan.angle_min                                  */
+  float angle_increment;  /* scan.angle_increment                            */
+  float range_min;        /* scan.range_min   (kept: range_min < r)          */
+  float range_max;        /* scan.range_max   (kept: r < range_max - 0.1)    */
+} hsb_scan_format;
+int hsb_set_scan_format(hsb_handle* h, const hsb_scan_format* fmt);
+/* rosLaserScanToDataContainer for one scan: ranges[n_beams] (host) -> compacted endpoints in
+ * level-0 cell units, beam order (host, capacity n_beams x 2), *out_n = number kept. */
+int hsb_scan_to_points(hsb_handle* h, const float* ranges, float* out_points_xy, int* out_n);
+/* hsb_match_batch / hsb_match_batch_device with the conversion fused into the match kernel's
+ * staging step: scan b is ranges[b*n_beams .. (b+1)*n_beams).  Halves the bytes per scan that have
+ * to cross PCIe (4 B per beam instead of 8 B per endpoint). */
+int hsb_match_batch_ranges(hsb_handle* h, int B, const float* hints_world, const float* ranges, float* out_poses_world,
+                           float* out_cov);
+int hsb_match_batch_ranges_device(hsb_handle* h, int B, const float* d_hints_world, const float* d_ranges,
+                                  float* d_out_poses_world, float* d_out_cov, void* stream);
+
 /* OccGridMapUtil::getCompleteHessianDerivs — map/OccGridMapUtil.h:64-104, one evaluation on one
  * level: `pose_map` and `points_level_xy` are in that level's cell units.  This is the finest
  * seam: the reference's own ScanMatcher can drive it one evaluation at a time. */

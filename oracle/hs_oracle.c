@@ -644,6 +644,28 @@ void hso_update_level(void* hv, int level, const float* pts_level, int n, const 
   maprep_on_map_updated(h);
 }
 
+/* HectorMappingRos::rosLaserScanToDataContainer — hector_mapping/src/HectorMappingRos.cpp:483-507.
+ * (That file needs ROS and cannot be compiled here, so this row of the path is pinned by this
+ * restatement only.)  `cos(angle)` / `sin(angle)` are called on a float with the <cmath> overloads
+ * visible, i.e. cosf / sinf.  out_xy has room for n_beams x 2; returns the number of endpoints. */
+int hso_scan_to_points(const float* ranges, int n_beams, float angle_min, float angle_increment, float range_min,
+                       float range_max, float scale_to_map, float* out_xy) {
+  float angle = angle_min;                         /* :487 */
+  float max_range_for_container = range_max - 0.1f; /* :493 */
+  int n = 0;
+  for (int i = 0; i < n_beams; ++i) {
+    float dist = ranges[i];
+    if ((dist > range_min) && (dist < max_range_for_container)) { /* :499 */
+      dist *= scale_to_map;                                       /* :501 */
+      out_xy[2 * n] = cosf(angle) * dist;
+      out_xy[2 * n + 1] = sinf(angle) * dist;
+      ++n;
+    }
+    angle += angle_increment; /* :505 */
+  }
+  return n;
+}
+
 /* ---- batch of independent matches (timing harness; same contract as hsref_match_batch) ------ */
 typedef struct {
   hso_t* master;

@@ -207,6 +207,17 @@ class Oracle:
         return poses, covs.reshape(B, 3, 3), float(secs)
 
 
+def scan_to_points(ranges, angle_min, angle_increment, range_min, range_max, scale_to_map):
+    """rosLaserScanToDataContainer (HectorMappingRos.cpp:483-507) by the C port. -> (n, 2) float32"""
+    lib = C.CDLL(PORT_LIB)
+    lib.hso_scan_to_points.restype = C.c_int
+    lib.hso_scan_to_points.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _f32p]
+    r = _f32(ranges).reshape(-1)
+    out = np.zeros(2 * r.size, np.float32)
+    n = lib.hso_scan_to_points(r, r.size, angle_min, angle_increment, range_min, range_max, scale_to_map, out)
+    return out[: 2 * n].reshape(n, 2).copy()
+
+
 def build_map_by_slam(orc: Oracle, world, scale_to_map: float = 20.0, noise_seed: int = 11, sigma: float = 0.01):
     """SLAM-mode map building, exactly what the reference node does: HectorSlamProcessor::update
     along the world's mapping poses, hint = ground truth, thresholds 0 so every scan writes.
