@@ -19,6 +19,7 @@
 #define HSB_MATCH_KERNEL_CUH
 
 #include "hsb_internal.h"
+#include "sincosf_glibc.h"
 
 namespace hsb {
 
@@ -51,38 +52,6 @@ __device__ __forceinline__ float normalize_angle(float angle) {
   float a = (float)r;
   if ((double)a > 3.14159265358979323846) a = (float)((double)a - two_pi);
   return a;
-}
-
-// sin/cos of the pose angle.  The reference calls sinf/cosf (OccGridMapUtil.h:70-71, :351); a
-// correctly rounded float result is reproduced by evaluating in double and rounding once.  Between
-// two evaluations the angle moves by at most the 0.2 rad clamp, so instead of a full double sincos
-// per evaluation (range reduction + two polynomials + slow path) the pair is ROTATED by the exact
-// difference d = psi_new - psi_old with 12th-order Taylor polynomials (|d| <= 0.25: truncation
-// < 3e-19, accumulated error over a level < 1e-15, i.e. ~1e-8 of a float ulp).
-__device__ __forceinline__ void sincos_advance(float psi_old, float psi_new, double& s, double& c) {
-  const double d = (double)psi_new - (double)psi_old;  // exact in double
-  if (!(fabs(d) <= 0.25)) {
-    sincos((double)psi_new, &s, &c);
-    return;
-  }
-  const double d2 = d * d;
-  double sn = -1.0 / 39916800.0;
-  sn = fma(sn, d2, 1.0 / 362880.0);
-  sn = fma(sn, d2, -1.0 / 5040.0);
-  sn = fma(sn, d2, 1.0 / 120.0);
-  sn = fma(sn, d2, -1.0 / 6.0);
-  sn = fma(sn * d2, d, d);
-  double cn = 1.0 / 479001600.0;
-  cn = fma(cn, d2, -1.0 / 3628800.0);
-  cn = fma(cn, d2, 1.0 / 40320.0);
-  cn = fma(cn, d2, -1.0 / 720.0);
-  cn = fma(cn, d2, 1.0 / 24.0);
-  cn = fma(cn, d2, -0.5);
-  cn = fma(cn, d2, 1.0);
-  const double c2 = fma(c, cn, -(s * sn));
-  const double s2 = fma(s, cn, c * sn);
-  c = c2;
-  s = s2;
 }
 
 // Eigen's fixed-size 3x3 inverse times vector (ScanMatcher.h:205 `H.inverse() * dTr`): cyclic
@@ -496,10 +465,9 @@ __global__ void __launch_bounds__(W * G * 32)
         const LevelRegs LR = level_regs(L);
         float ex, ey, epsi = wpsi;
         affine_apply_exact(L.mtw, wx, wy, ex, ey);  // ScanMatcher.h:70 getMapCoordsPose
-        double sd, cd;
-        sincos((double)epsi, &sd, &cd);              // OccGridMapUtil.h:70-71 (sinf/cosf, correctly rounded)
         for (int e = 0; e < L.evals; ++e) {          // ScanMatcher.h:74 + :94-97
-          const float cs = (float)cd * L.pt_scale, ss = (float)sd * L.pt_scale;
+          // OccGridMapUtil.h:70-71 and Rotation2Df (:351): sinf/cosf exactly as glibc evaluates them
+          const float cs = cosf_glibc(epsi) * L.pt_scale, ss = sinf_glibc(epsi) * L.pt_scale;
           Acc a;
           acc_zero(a);
           if (staged)
@@ -541,9 +509,7 @@ __global__ void __launch_bounds__(W * G * 32)
             else if (d2 < -0.2f) d2 = -0.2f;
             ex = __fadd_rn(ex, d0);              // :217
             ey = __fadd_rn(ey, d1);
-            const float npsi = __fadd_rn(epsi, d2);
-            if (e + 1 < L.evals) sincos_advance(epsi, npsi, sd, cd);
-            epsi = npsi;
+            epsi = __fadd_rn(epsi, d2);
           }
         }
         epsi = normalize_angle(epsi);                 // ScanMatcher.h:170
@@ -584,9 +550,7 @@ __global__ void __launch_bounds__(256)
     hessian_kernel(const HsbLevelDev L, const float2* __restrict__ pts, int n, float px, float py, float ppsi,
                    float* __restrict__ out12) {
   __shared__ float red[8][12];
-  double sd, cd;
-  sincos((double)ppsi, &sd, &cd);
-  const float cs = (float)cd, ss = (float)sd;
+  const float cs = cosf_glibc(ppsi), ss = sinf_glibc(ppsi);
   Acc a;
   acc_zero(a);
   eval_points<MODE, HSB_UNROLL>(level_regs(L), pts, threadIdx.x, blockDim.x, n, cs, ss, px, py, a);

@@ -25,6 +25,7 @@
 #define HSB_UPDATE_KERNEL_CUH
 
 #include "hsb_internal.h"
+#include "sincosf_glibc.h"
 
 namespace hsb {
 
@@ -103,9 +104,7 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Hsb
     mx = __fadd_rn(__fmul_rn(m[0], P.pose_world[0]), __fadd_rn(__fmul_rn(m[1], P.pose_world[1]), m[2]));
     my = __fadd_rn(__fmul_rn(m[3], P.pose_world[0]), __fadd_rn(__fmul_rn(m[4], P.pose_world[1]), m[5]));
   }
-  double sd, cd;
-  sincos((double)P.pose_world[2], &sd, &cd);
-  const float c = (float)cd, s = (float)sd;
+  const float c = cosf_glibc(P.pose_world[2]), s = sinf_glibc(P.pose_world[2]);  // Rotation2Df, as glibc
   // beam start = (int)(T * origo + 0.5)                                   (:134-137)
   const float ox = L.origo_x * L.pt_scale, oy = L.origo_y * L.pt_scale;
   const float bxf = __fadd_rn(__fmul_rn(c, ox), __fadd_rn(__fmul_rn(-s, oy), mx));
