@@ -26,7 +26,7 @@ EXPORTED = [
     "hsb_upload_level", "hsb_download_level", "hsb_download_prob", "hsb_level_logodds_device_ptr",
     "hsb_refresh_level", "hsb_last_error", "hsb_status_string", "hsb_get_launch_count", "hsb_get_gather_mode",
     "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
-    "hsb_match_batch_ranges_device",
+    "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch",
 ]
 
 
@@ -111,6 +111,8 @@ def load_library() -> C.CDLL:
     sig("hsb_scan_to_points", i, vp, vp, vp, ip)
     sig("hsb_match_batch_ranges", i, vp, i, vp, vp, vp, vp)
     sig("hsb_match_batch_ranges_device", i, vp, i, vp, vp, vp, vp, vp)
+    sig("hsb_download_occupancy", i, vp, i, vp)
+    sig("hsb_likelihood_batch", i, vp, i, i, vp, vp, vp, i, vp)
     _lib = L
     return L
 
@@ -347,6 +349,30 @@ class MapRepB200:
         sx, sy, _ = self.level_info(level)
         out = np.zeros((sy, sx), np.float32)
         self._check(self.lib.hsb_download_prob(self.h, level, out.ctypes.data))
+        return out
+
+    def download_occupancy(self, level: int) -> np.ndarray:
+        """nav_msgs/OccupancyGrid data of one level: 0 free, 100 occupied, -1 unknown."""
+        sx, sy, _ = self.level_info(level)
+        out = np.zeros((sy, sx), np.int8)
+        self._check(self.lib.hsb_download_occupancy(self.h, level, out.ctypes.data))
+        return out
+
+    def likelihood_batch(self, level: int, poses_world, points_xy, offsets=None) -> np.ndarray:
+        """getLikelihoodForState for B world poses (scan layout as match_batch)."""
+        poses = _f32(poses_world).reshape(-1, 3)
+        pts = _f32(points_xy).reshape(-1, 2)
+        B = poses.shape[0]
+        n_shared = 0
+        offp = None
+        if offsets is None:
+            n_shared = pts.shape[0]
+        else:
+            offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+            offp = offsets.ctypes.data
+        out = np.zeros(B, np.float32)
+        self._check(self.lib.hsb_likelihood_batch(self.h, level, B, poses.ctypes.data, pts.ctypes.data if pts.size else None,
+                                                  offp, n_shared, out.ctypes.data))
         return out
 
     def level_logodds_device_ptr(self, level: int) -> int:

@@ -54,7 +54,7 @@ struct hsb_handle {
   // "containers of the last match" (MapRepMultiMap::dataContainers) and the update scan
   DevBuf d_last_pts, d_upd_pts;
   // raw-range input (N2)
-  DevBuf d_beam_cs, d_ranges;
+  DevBuf d_beam_cs, d_ranges, d_occ;
   hsb_scan_format fmt = hsb_scan_format();
   bool fmt_set = false;
   int last_n = 0;
@@ -452,7 +452,7 @@ int hsb_destroy(hsb_handle* h) {
   cudaDeviceSynchronize();
   for (int l = 0; l < HSB_MAX_LEVELS; ++l) destroy_level(h, h->lv[l]);
   DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_last_pts, &h->d_upd_pts,
-                    &h->d_beam_cs, &h->d_ranges};
+                    &h->d_beam_cs, &h->d_ranges, &h->d_occ};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -933,6 +933,58 @@ int hsb_download_prob(hsb_handle* h, int level, float* out) {
     HSB_CUDA(h, cudaMemcpyAsync(out, L.prob, (size_t)L.sx * L.sy * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   }
   HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HSB_OK;
+}
+
+int hsb_download_occupancy(hsb_handle* h, int level, int8_t* out) {
+  if (!h || level < 0 || level >= h->levels || !out) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  const size_t n = (size_t)L.sx * L.sy;
+  int s = ensure(h, h->d_occ, n);
+  if (s != HSB_OK) return s;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  hsb::occupancy_kernel<<<blocks, 256, 0, h->stream>>>(L.logodds, static_cast<int8_t*>(h->d_occ.p), n);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  HSB_CUDA(h, cudaMemcpyAsync(out, h->d_occ.p, n, cudaMemcpyDeviceToHost, h->stream));
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HSB_OK;
+}
+
+int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses, const float* pts, const int* offsets,
+                         int n_shared, float* out) {
+  if (!h || level < 0 || level >= h->levels || B < 0 || !poses || !out) return HSB_ERR_INVALID_ARG;
+  if (B == 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  size_t total = offsets ? (size_t)offsets[B] : (size_t)(n_shared > 0 ? n_shared : 0);
+  if (total > 0 && !pts) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  int s;
+  if ((s = ensure(h, h->d_hints, (size_t)B * 12)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_pts, total * 8 + 16)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_offsets, (size_t)(B + 1) * 4)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_poses, (size_t)B * 12)) != HSB_OK) return s;
+  cudaStream_t st = h->stream;
+  HSB_CUDA(h, cudaMemcpyAsync(h->d_hints.p, poses, (size_t)B * 12, cudaMemcpyHostToDevice, st));
+  if (total > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_pts.p, pts, total * 8, cudaMemcpyHostToDevice, st));
+  if (offsets) HSB_CUDA(h, cudaMemcpyAsync(h->d_offsets.p, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+  HsbLevelDev L;
+  fill_level_dev(h, level, L);
+  int blocks = std::min((B + 3) / 4, h->sm_count * 16);
+  const int* d_off = offsets ? static_cast<const int*>(h->d_offsets.p) : nullptr;
+  float* d_out = static_cast<float*>(h->d_poses.p);
+  if (h->gather_mode == HSB_GATHER_TEX)
+    hsb::likelihood_kernel<hsb::MODE_TEX><<<blocks, 128, 0, st>>>(L, B, static_cast<const float*>(h->d_hints.p),
+                                                                  static_cast<const float2*>(h->d_pts.p), d_off,
+                                                                  offsets ? 0 : n_shared, d_out);
+  else
+    hsb::likelihood_kernel<hsb::MODE_LDG><<<blocks, 128, 0, st>>>(L, B, static_cast<const float*>(h->d_hints.p),
+                                                                  static_cast<const float2*>(h->d_pts.p), d_off,
+                                                                  offsets ? 0 : n_shared, d_out);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  HSB_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));
   return HSB_OK;
 }
 

@@ -544,6 +544,42 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) *out_n = n;
 }
 
+// N3: OccGridMapUtil::getLikelihoodForState (OccGridMapUtil.h:189-221) for a batch of poses, one warp
+// per pose.  interpMapValue (:233-285) is the value-only bilinear interpolation: 0 out of bounds.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+    likelihood_kernel(const HsbLevelDev L, int B, const float* __restrict__ poses_world, const float2* __restrict__ pts_all,
+                      const int* __restrict__ offsets, int n_shared, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const LevelRegs LR = level_regs(L);
+  for (int b = warp; b < B; b += nwarps) {
+    int beg = 0, n = n_shared;
+    if (offsets) {
+      beg = offsets[b];
+      n = offsets[b + 1] - beg;
+    }
+    const float2* pts = pts_all + beg;
+    float ex, ey;
+    affine_apply_exact(L.mtw, poses_world[3 * b], poses_world[3 * b + 1], ex, ey);
+    const float psi = poses_world[3 * b + 2];
+    const float cs = cosf_glibc(psi) * L.pt_scale, ss = sinf_glibc(psi) * L.pt_scale;
+    float residual = 0.0f;
+    for (int i = lane; i < n; i += 32) {
+      const float2 p = pts[i];
+      PointPre pre;
+      point_address<MODE>(LR, p.x, p.y, true, cs, ss, ex, ey, pre);
+      const float4 v = point_fetch<MODE>(LR, pre);
+      const float xi = 1.0f - pre.fx, yi = 1.0f - pre.fy;
+      const float m = (v.x * xi + v.y * pre.fx) * yi + (v.z * xi + v.w * pre.fx) * pre.fy;  // :282-284
+      residual += pre.inside ? (1.0f - m) : 1.0f;                                         // :216-217
+    }
+    residual = warp_sum(residual);
+    if (lane == 0) out[b] = 1.0f - residual / (float)n;  // getLikelihoodForResidual :203-209
+  }
+}
+
 // Single evaluation (the getCompleteHessianDerivs seam): one CTA of 256 threads.
 template <int MODE>
 __global__ void __launch_bounds__(256)

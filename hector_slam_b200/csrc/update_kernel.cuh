@@ -64,6 +64,15 @@ __global__ void clear_level_kernel(float* __restrict__ logodds, float* __restric
   }
 }
 
+// N1: nav_msgs/OccupancyGrid values as HectorMappingRos::publishMap derives them
+// (hector_mapping/src/HectorMappingRos.cpp:448-468; isFree / isOccupied GridMapLogOdds.h:76-84).
+__global__ void occupancy_kernel(const float* __restrict__ logodds, int8_t* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float l = logodds[i];
+    out[i] = l < 0.0f ? (int8_t)0 : (l > 0.0f ? (int8_t)100 : (int8_t)-1);
+  }
+}
+
 __device__ __forceinline__ void claim_and_apply(const HsbUpdateLevelDev& L, unsigned off, float lf, float lo) {
   const uint32_t base = L.stamp_base;
   const uint32_t v = __ldcg(L.stamp + off);

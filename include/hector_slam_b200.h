@@ -189,6 +189,21 @@ int hsb_download_prob(hsb_handle* h, int level, float* prob_host_out);
 void* hsb_level_logodds_device_ptr(hsb_handle* h, int level);
 int hsb_refresh_level(hsb_handle* h, int level, void* stream);
 
+/* ---- after the path: what the node does with the results -------------------------------------*/
+/* nav_msgs/OccupancyGrid cell values of one level, as HectorMappingRos::publishMap derives them
+ * (hector_mapping/src/HectorMappingRos.cpp:448-468): 0 where the cell is free (log-odds < 0,
+ * GridMapLogOdds.h:81-84), 100 where occupied (> 0, :76-79), -1 otherwise.  Thresholded on the
+ * device, so one byte per cell crosses PCIe instead of four.  out: [size_y][size_x] int8 (host). */
+int hsb_download_occupancy(hsb_handle* h, int level, int8_t* occupancy_host_out);
+/* OccGridMapUtil::getLikelihoodForState — map/OccGridMapUtil.h:189-221: 1 - residual / n with
+ * residual = sum_i (1 - interpMapValue(T(state) * p_i)) (an out-of-map endpoint counts 1), for B
+ * poses (world frame; converted with getMapCoordsPose of `level`) against scan b of the batch
+ * (same scan layout as hsb_match_batch: offsets == NULL -> one shared scan of n_shared points,
+ * given in LEVEL-0 cell units and scaled by 2^-level like the matcher does).  Ranks relocalisation
+ * hypotheses; the reference only uses it in its (dead) sigma-point covariance.  Host buffers. */
+int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses_world, const float* points_xy,
+                         const int* offsets, int n_shared, float* out_likelihood);
+
 /* ---- diagnostics ----------------------------------------------------------------------------*/
 const char* hsb_last_error(const hsb_handle* h);
 const char* hsb_status_string(int status);

@@ -644,6 +644,41 @@ void hso_update_level(void* hv, int level, const float* pts_level, int n, const 
   maprep_on_map_updated(h);
 }
 
+/* OccGridMapUtil.h:233-285 interpMapValue */
+static float interp_value(level_t* L, float cx, float cy) {
+  if ((cx < 0.0f) || (cx > L->limit_x) || (cy < 0.0f) || (cy > L->limit_y)) return 0.0f;
+  int ix = (int)cx, iy = (int)cy;
+  float fx = cx - (float)ix, fy = cy - (float)iy;
+  int size_x = L->size_x;
+  int index = iy * size_x + ix;
+  float i0 = cached_prob(L, index);
+  ++index;
+  float i1 = cached_prob(L, index);
+  index += size_x - 1;
+  float i2 = cached_prob(L, index);
+  ++index;
+  float i3 = cached_prob(L, index);
+  float x_inv = 1.0f - fx, y_inv = 1.0f - fy;
+  return ((i0 * x_inv + i1 * fx) * y_inv) + ((i2 * x_inv + i3 * fx) * fy);
+}
+
+/* OccGridMapUtil.h:189-221 getLikelihoodForState = getLikelihoodForResidual(getResidualForState) */
+float hso_likelihood(void* hv, int level, const float pose_map[3], const float* pts_level, int n) {
+  hso_t* h = (hso_t*)hv;
+  level_t* L = &h->lv[level];
+  affine2 T;
+  transform_for_state(pose_map, &T);
+  float residual = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    float qx, qy;
+    affine2_apply(&T, pts_level[2 * i], pts_level[2 * i + 1], &qx, &qy);
+    float funval = 1.0f - interp_value(L, qx, qy); /* :216 */
+    residual += funval;
+  }
+  float sizef = (float)n; /* :205-206 */
+  return 1 - (residual / sizef);
+}
+
 /* HectorMappingRos::rosLaserScanToDataContainer — hector_mapping/src/HectorMappingRos.cpp:483-507.
  * (That file needs ROS and cannot be compiled here, so this row of the path is pinned by this
  * restatement only.)  `cos(angle)` / `sin(angle)` are called on a float with the <cmath> overloads

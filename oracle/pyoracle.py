@@ -90,6 +90,7 @@ class Oracle:
         sig("match_level", None, vp, i, _f32p, _f32p, i, i, _f32p, _f32p)
         sig("update_level", None, vp, i, _f32p, i, _f32p, _f32p)
         sig("match_batch", C.c_double, vp, i, _f32p, _f32p, _i32p, _f32p, _f32p, i)
+        sig("likelihood", f, vp, i, _f32p, _f32p, i)
 
     def close(self):
         if getattr(self, "h", None):
@@ -183,6 +184,11 @@ class Oracle:
         H, d = np.zeros(9, np.float32), np.zeros(3, np.float32)
         self._fn("hessian_derivs")(self.h, level, _f32(pose_map), pts, pts.shape[0], H, d)
         return H.reshape(3, 3), d
+
+    def likelihood(self, level: int, pose_map, pts_level) -> float:
+        """OccGridMapUtil::getLikelihoodForState (state and points in the level's cell units)."""
+        pts = _f32(pts_level).reshape(-1, 2)
+        return float(self._fn("likelihood")(self.h, level, _f32(pose_map), pts, pts.shape[0]))
 
     def match_level(self, level: int, hint_world, pts_level, max_iterations: int):
         """ScanMatcher::matchData on one level (1 + max_iterations evaluations)."""

@@ -247,6 +247,16 @@ void hsref_update_level(void* hv, int level, const float* pts_level, int n, cons
   h->proc->rep()->onMapUpdated();
 }
 
+// OccGridMapUtil::getLikelihoodForState — map/OccGridMapUtil.h:189-221 (state in the level's cells)
+float hsref_likelihood(void* hv, int level, const float pose_map[3], const float* pts_level, int n) {
+  Handle* h = static_cast<Handle*>(hv);
+  hectorslam::GridMap& g = h->proc->grid(level);
+  hectorslam::OccGridMapUtilConfig<hectorslam::GridMap> util(&g);
+  hectorslam::DataContainer dc;
+  fill(dc, pts_level, n, 0);
+  return util.getLikelihoodForState(Eigen::Vector3f(pose_map[0], pose_map[1], pose_map[2]), dc);
+}
+
 // Batch of independent matches against the handle's current (frozen) map.
 // nthreads <= 1: the handle's own processor, calling thread.
 // nthreads  > 1: OccGridMapUtil is not re-entrant (mutable members, OccGridMapUtil.h:376-378), so

@@ -1,0 +1,95 @@
+"""GPU: the rows after / around the path that were widened into.
+  N1  log-odds -> nav_msgs/OccupancyGrid int8 (HectorMappingRos::publishMap, src/HectorMappingRos.cpp:448-468)
+  N3  pose likelihood (OccGridMapUtil::getLikelihoodForState, map/OccGridMapUtil.h:189-221), batched —
+      ranks the relocalisation hypotheses of BASELINE config 4."""
+import numpy as np
+import pytest
+
+from conftest import golden_planes, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_occupancy_export_bit_exact(hsb_lib, mode):
+    from hector_slam_b200 import capi
+
+    g = load_golden("match3.npz")
+    rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, gather_mode=mode)
+    planes = golden_planes(g)
+    planes[0][5, 7] = np.float32(-0.0)   # isFree / isOccupied are strict comparisons with 0
+    planes[0][5, 8] = np.float32(1e-30)
+    planes[0][5, 9] = np.float32(-1e-30)
+    for l, p in enumerate(planes):
+        rep.upload_level(l, p)
+    for l, p in enumerate(planes):
+        want = np.full(p.shape, -1, np.int8)
+        want[p < 0] = 0
+        want[p > 0] = 100
+        got = rep.download_occupancy(l)
+        assert got.dtype == np.int8 and np.array_equal(got, want)
+    assert got.min() == -1 and (rep.download_occupancy(0) == 100).sum() > 1000
+    rep.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_likelihood_batch(hsb_lib, pyoracle, oracle_kinds, mode):
+    from hector_slam_b200 import capi
+
+    g = load_golden("match3.npz")
+    kind = "reference" if "reference" in oracle_kinds else "port"
+    orc = pyoracle.Oracle(kind, float(g["res"]), int(g["size"]), 3)
+    rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, gather_mode=mode)
+    for l, p in enumerate(golden_planes(g)):
+        rep.upload_level(l, p)
+        orc.set_logodds(l, p)
+    K = g["scans"].shape[0]
+    pts = g["scans"].reshape(-1, 2)
+    offs = (np.arange(K + 1) * g["scans"].shape[1]).astype(np.int32)
+    poses = g["hints"].copy()
+    poses[3, 0] += 40.0                      # far outside the map: every endpoint counts 1 -> likelihood 0
+    for l in range(3):
+        got = rep.likelihood_batch(l, poses, pts, offs)
+        want = np.float32([orc.likelihood(l, orc.map_coords_pose(l, poses[k]),
+                                          (g["scans"][k] * np.float32(2.0 ** -l)).astype(np.float32)) for k in range(K)])
+        assert np.abs(got - want).max() <= 2e-6, (l, np.abs(got - want).max())
+        assert got[3] == 0.0
+    # ranking hypotheses of ONE scan: the matched pose scores higher than its perturbed hint
+    hyp = np.stack([g["hints"][0], g["ref_poses"][0], g["truth"][0].astype(np.float32)])
+    sc = rep.likelihood_batch(0, hyp, g["scans"][0], None)
+    assert sc[1] > sc[0] and sc[2] > sc[0]
+    rep.close()
+    orc.close()
+
+
+def test_config4_best_hypothesis_by_likelihood(hsb_lib, pyoracle):
+    """Config 4 end to end on one GPU: match 8192 hypotheses of one scan, score the results with the
+    likelihood kernel, pick the best — it must be the in-basin fixed point (== the oracle's answer)."""
+    from hector_slam_b200 import capi, synth
+
+    world = synth.World(1, seed=1234)
+    g = load_golden("match3.npz")
+    rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+    orc = pyoracle.Oracle("port", float(g["res"]), int(g["size"]), 3)
+    orc.set_update_factors(0.4, 0.9)
+    for l, p in enumerate(golden_planes(g)):
+        rep.upload_level(l, p)
+        orc.set_logodds(l, p)
+    truth, scan = g["truth"][2], g["scans"][2]
+    rng = np.random.default_rng(9)
+    B = 8192
+    hyp = np.tile(truth, (B, 1))
+    hyp[:, 0] += rng.uniform(-2.0, 2.0, B)
+    hyp[:, 1] += rng.uniform(-2.0, 2.0, B)
+    hyp[:, 2] += rng.uniform(-0.5, 0.5, B)
+    hyp = hyp.astype(np.float32)
+    poses, _ = rep.match_batch(hyp, scan, None)
+    finite = np.all(np.isfinite(poses), axis=1)
+    score = np.full(B, -1.0, np.float32)
+    score[finite] = rep.likelihood_batch(0, poses[finite], scan, None)
+    best = poses[int(np.argmax(score))]
+    want, _ = orc.match(truth.astype(np.float32), scan)
+    assert np.abs(best[:2] - want[:2]).max() < 5e-3 and abs(best[2] - want[2]) < 5e-3, (best, want)
+    assert np.abs(best[:2] - truth[:2]).max() < 0.02
+    rep.close()
+    orc.close()
