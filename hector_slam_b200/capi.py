@@ -27,6 +27,7 @@ EXPORTED = [
     "hsb_refresh_level", "hsb_last_error", "hsb_status_string", "hsb_get_launch_count", "hsb_get_gather_mode",
     "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
     "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch",
+    "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device",
 ]
 
 
@@ -113,6 +114,9 @@ def load_library() -> C.CDLL:
     sig("hsb_match_batch_ranges_device", i, vp, i, vp, vp, vp, vp, vp)
     sig("hsb_download_occupancy", i, vp, i, vp)
     sig("hsb_likelihood_batch", i, vp, i, i, vp, vp, vp, i, vp)
+    sig("hsb_get_dirty_rect", i, vp, i, vp, i)
+    sig("hsb_pack_rect_device", i, vp, i, vp, vp, vp)
+    sig("hsb_unpack_rect_device", i, vp, i, vp, vp, vp)
     _lib = L
     return L
 
@@ -374,6 +378,21 @@ class MapRepB200:
         self._check(self.lib.hsb_likelihood_batch(self.h, level, B, poses.ctypes.data, pts.ctypes.data if pts.size else None,
                                                   offp, n_shared, out.ctypes.data))
         return out
+
+    def get_dirty_rect(self, level: int, reset: bool = False):
+        """(x0, y0, x1, y1) inclusive of the cells written since the last reset, or None."""
+        r = (C.c_int * 4)()
+        self._check(self.lib.hsb_get_dirty_rect(self.h, level, r, int(reset)))
+        rect = tuple(int(v) for v in r)
+        return None if rect[2] < rect[0] else rect
+
+    def pack_rect_device(self, level: int, rect, d_buf: int, stream: int = 0):
+        r = (C.c_int * 4)(*rect)
+        self._check(self.lib.hsb_pack_rect_device(self.h, level, r, d_buf, stream))
+
+    def unpack_rect_device(self, level: int, rect, d_buf: int, stream: int = 0):
+        r = (C.c_int * 4)(*rect)
+        self._check(self.lib.hsb_unpack_rect_device(self.h, level, r, d_buf, stream))
 
     def level_logodds_device_ptr(self, level: int) -> int:
         return int(self.lib.hsb_level_logodds_device_ptr(self.h, level) or 0)

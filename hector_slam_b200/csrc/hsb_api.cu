@@ -2,6 +2,7 @@
 // kernels in match_kernel.cuh / update_kernel.cuh.  No torch types, no CPU fallback: every entry
 // point that computes something launches a CUDA kernel or fails with an error code.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -29,6 +30,7 @@ struct Level {
   cudaTextureObject_t tex = 0;
   cudaSurfaceObject_t surf = 0;
   int evals = 0;
+  int* dirty = nullptr;  // device {xmin, ymin, xmax, ymax}
 };
 
 struct DevBuf {
@@ -165,6 +167,10 @@ int clear_level(hsb_handle* h, int level, cudaStream_t st) {
   h->launches++;
   HSB_CUDA(h, cudaGetLastError());
   L.stamp_base = 0;
+  if (L.dirty) {
+    const int clean[4] = {INT_MAX, INT_MAX, -1, -1};
+    HSB_CUDA(h, cudaMemcpyAsync(L.dirty, clean, sizeof(clean), cudaMemcpyHostToDevice, st));
+  }
   return HSB_OK;
 }
 
@@ -297,6 +303,7 @@ int destroy_level(hsb_handle* h, Level& L) {
   if (L.logodds) cudaFree(L.logodds);
   if (L.prob) cudaFree(L.prob);
   if (L.stamp) cudaFree(L.stamp);
+  if (L.dirty) cudaFree(L.dirty);
   L = Level();
   (void)h;
   return HSB_OK;
@@ -417,6 +424,11 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
     HSB_CUDA_C(cudaMalloc(&L.logodds, n * sizeof(float)));
     HSB_CUDA_C(cudaMalloc(&L.prob, n * sizeof(float)));
     HSB_CUDA_C(cudaMalloc(&L.stamp, n * sizeof(uint32_t)));
+    HSB_CUDA_C(cudaMalloc(&L.dirty, 4 * sizeof(int)));
+    {
+      const int clean[4] = {INT_MAX, INT_MAX, -1, -1};
+      HSB_CUDA_C(cudaMemcpy(L.dirty, clean, sizeof(clean), cudaMemcpyHostToDevice));
+    }
     if (h->gather_mode == HSB_GATHER_TEX) {
       cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
       HSB_CUDA_C(cudaMallocArray(&L.arr, &desc, dx, dy, cudaArrayTextureGather | cudaArraySurfaceLoadStore));
@@ -823,6 +835,7 @@ static void fill_update_level(hsb_handle* h, int l, HsbUpdateLevelDev& d) {
   d.sx = L.sx;
   d.sy = L.sy;
   memcpy(d.mtw, L.mtw, sizeof(d.mtw));
+  d.dirty = L.dirty;
 }
 
 int hsb_update_by_scan(hsb_handle* h, const float* pts, int n, const float origo[2], const float pose[3]) {
@@ -985,6 +998,57 @@ int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses, co
   HSB_CUDA(h, cudaGetLastError());
   HSB_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   HSB_CUDA(h, cudaStreamSynchronize(st));
+  return HSB_OK;
+}
+
+int hsb_get_dirty_rect(hsb_handle* h, int level, int rect[4], int reset) {
+  if (!h || level < 0 || level >= h->levels || !rect) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  HSB_CUDA(h, cudaMemcpyAsync(rect, L.dirty, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (reset) {
+    const int clean[4] = {INT_MAX, INT_MAX, -1, -1};
+    HSB_CUDA(h, cudaMemcpyAsync(L.dirty, clean, sizeof(clean), cudaMemcpyHostToDevice, h->stream));
+    HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return HSB_OK;
+}
+
+static int check_rect(hsb_handle* h, const Level& L, const int rect[4]) {
+  if (rect[0] < 0 || rect[1] < 0 || rect[2] >= L.sx || rect[3] >= L.sy || rect[2] < rect[0] || rect[3] < rect[1])
+    return fail(h, HSB_ERR_INVALID_ARG, "rectangle outside the level or empty");
+  return HSB_OK;
+}
+
+int hsb_pack_rect_device(hsb_handle* h, int level, const int rect[4], float* d_buf, void* stream) {
+  if (!h || level < 0 || level >= h->levels || !rect || !d_buf) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  int s = check_rect(h, L, rect);
+  if (s != HSB_OK) return s;
+  const int w = rect[2] - rect[0] + 1, hgt = rect[3] - rect[1] + 1;
+  const size_t n = (size_t)w * hgt;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  hsb::pack_rect_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(L.logodds, L.sx, rect[0], rect[1], w, hgt, d_buf);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  return HSB_OK;
+}
+
+int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const float* d_buf, void* stream) {
+  if (!h || level < 0 || level >= h->levels || !rect || !d_buf) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  int s = check_rect(h, L, rect);
+  if (s != HSB_OK) return s;
+  const int w = rect[2] - rect[0] + 1, hgt = rect[3] - rect[1] + 1;
+  const size_t n = (size_t)w * hgt;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  hsb::unpack_rect_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(L.logodds, L.prob, L.surf, L.sx, rect[0], rect[1], w, hgt,
+                                                                    d_buf);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
   return HSB_OK;
 }
 

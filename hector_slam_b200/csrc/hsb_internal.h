@@ -55,6 +55,7 @@ struct HsbUpdateLevelDev {
   float origo_x, origo_y;    // already in the units of `pts` before pt_scale
   uint32_t stamp_base;       // this scan's stamps: base+1 free, base+2 occupied, base+3 applied
   int active;
+  int* dirty;                // {xmin, ymin, xmax, ymax} of cells written since the last reset (device)
 };
 
 struct HsbUpdateParams {

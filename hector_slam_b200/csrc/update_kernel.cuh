@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Hsb
   if ((x0 < 0) || (x0 >= L.sx) || (y0 < 0) || (y0 >= L.sy)) return;  // :176 (same start for all beams)
   const unsigned start = (unsigned)y0 * (unsigned)L.sx + (unsigned)x0;
   const uint32_t free_s = L.stamp_base + 1u, occ_s = L.stamp_base + 2u;
+  // dirty rectangle (for tile replication to map replicas): every written cell lies on a segment
+  // between the start cell and an end cell, so the box of those end points covers them all
+  int bx0 = x0, by0 = y0, bx1 = x0, by1 = y0;
+  bool wrote = false;
 
   for (int b = warp0; b < L.n; b += warp_stride) {
     const float2 pt = L.pts[b];
@@ -157,6 +161,10 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Hsb
         if (__ldcg(L.stamp + off) < free_s) atomicMax(L.stamp + off, free_s);   // bresenhamCellFree :216-224
       }
     }
+    if (!APPLY) {
+      bx0 = min(bx0, x1); by0 = min(by0, y1); bx1 = max(bx1, x1); by1 = max(by1, y1);
+      wrote = true;
+    }
     if (lane == 0) {
       const unsigned end = (unsigned)y1 * (unsigned)L.sx + (unsigned)x1;        // :211-212
       if (APPLY) {
@@ -165,6 +173,36 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Hsb
         atomicMax(L.stamp + end, occ_s);                                        // bresenhamCellOcc :226-241
       }
     }
+  }
+  if (!APPLY && wrote && lane == 0 && L.dirty) {  // one set of atomics per warp
+    atomicMin(L.dirty + 0, bx0);
+    atomicMin(L.dirty + 1, by0);
+    atomicMax(L.dirty + 2, bx1);
+    atomicMax(L.dirty + 3, by1);
+  }
+}
+
+// Dirty-rectangle transport: pack the log-odds of rect = {x0, y0, x1, y1} (inclusive) row by row
+// into a contiguous buffer / write such a buffer back and refresh P (and the texture twin) there.
+__global__ void pack_rect_kernel(const float* __restrict__ logodds, int sx, int x0, int y0, int w, int hgt,
+                                 float* __restrict__ buf) {
+  const size_t n = (size_t)w * hgt;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (size_t)w), c = (int)(i - (size_t)r * w);
+    buf[i] = logodds[(size_t)(y0 + r) * sx + (x0 + c)];
+  }
+}
+__global__ void unpack_rect_kernel(float* __restrict__ logodds, float* __restrict__ prob, cudaSurfaceObject_t surf, int sx,
+                                   int x0, int y0, int w, int hgt, const float* __restrict__ buf) {
+  const size_t n = (size_t)w * hgt;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (size_t)w), c = (int)(i - (size_t)r * w);
+    const size_t off = (size_t)(y0 + r) * sx + (x0 + c);
+    const float l = buf[i];
+    logodds[off] = l;
+    const float p = prob_from_logodds(l);
+    prob[off] = p;
+    if (surf) surf2Dwrite(p, surf, (x0 + c) * (int)sizeof(float), y0 + r);
   }
 }
 

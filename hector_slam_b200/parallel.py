@@ -88,3 +88,36 @@ def match_sharded(match_fn, hints, pts, offsets, group=None, device="cpu"):
     cov_t = torch.as_tensor(np.ascontiguousarray(cov, dtype=np.float32), device=device).reshape(hi - lo, 9)
     B = hints.shape[0]
     return gather_rows(poses_t, B, group), gather_rows(cov_t, B, group).reshape(B, 3, 3)
+
+
+def broadcast_dirty_tiles(rep, device, src: int = 0, group=None) -> int:
+    """After the owner rank (`src`) has written its map (hsb_update_by_scan), ship what changed to
+    the replicas: per level the dirty rectangle (4 ints) and its log-odds rows (one broadcast
+    each); replicas write the rows into their planes and refresh the probabilities there.
+    Returns the number of cells shipped.  No-op without a process group."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        for l in range(rep.getMapLevels()):
+            rep.get_dirty_rect(l, reset=True)
+        return 0
+    rank = dist.get_rank(group)
+    shipped = 0
+    stream = torch.cuda.current_stream(device).cuda_stream if torch.device(device).type == "cuda" else 0
+    for l in range(rep.getMapLevels()):
+        rect_t = torch.tensor([0, 0, -1, -1], dtype=torch.int32, device=device)  # clean: x1 < x0
+        if rank == src:
+            r = rep.get_dirty_rect(l, reset=True)
+            if r is not None:
+                rect_t = torch.tensor(r, dtype=torch.int32, device=device)
+        dist.broadcast(rect_t, src=src, group=group)
+        rect = [int(v) for v in rect_t.tolist()]
+        if rect[2] < rect[0]:
+            continue
+        n = (rect[2] - rect[0] + 1) * (rect[3] - rect[1] + 1)
+        buf = torch.empty(n, dtype=torch.float32, device=device)
+        if rank == src:
+            rep.pack_rect_device(l, rect, buf.data_ptr(), stream)
+        dist.broadcast(buf, src=src, group=group)
+        if rank != src:
+            rep.unpack_rect_device(l, rect, buf.data_ptr(), stream)
+        shipped += n
+    return shipped

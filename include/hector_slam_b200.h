@@ -189,6 +189,17 @@ int hsb_download_prob(hsb_handle* h, int level, float* prob_host_out);
 void* hsb_level_logodds_device_ptr(hsb_handle* h, int level);
 int hsb_refresh_level(hsb_handle* h, int level, void* stream);
 
+/* Dirty-rectangle replication (multi-GPU: the owner of the map writes, replicas receive tiles).
+ * hsb_get_dirty_rect: bounding box {x0, y0, x1, y1} (inclusive, level cells) of everything
+ * hsb_update_by_scan wrote on `level` since the last reset (x1 < x0: nothing); `reset` != 0 clears
+ * it.  hsb_pack_rect_device copies that rectangle of the log-odds plane row by row into a
+ * contiguous device buffer ((x1-x0+1)*(y1-y0+1) floats) — the payload of an NCCL broadcast;
+ * hsb_unpack_rect_device writes such a buffer into this handle's plane and refreshes the
+ * probability plane (and texture twin) of the rectangle.  Asynchronous on `stream`. */
+int hsb_get_dirty_rect(hsb_handle* h, int level, int rect[4], int reset);
+int hsb_pack_rect_device(hsb_handle* h, int level, const int rect[4], float* d_buf, void* stream);
+int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const float* d_buf, void* stream);
+
 /* ---- after the path: what the node does with the results -------------------------------------*/
 /* nav_msgs/OccupancyGrid cell values of one level, as HectorMappingRos::publishMap derives them
  * (hector_mapping/src/HectorMappingRos.cpp:448-468): 0 where the cell is free (log-odds < 0,

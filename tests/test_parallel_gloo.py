@@ -67,6 +67,45 @@ def _worker(rank, world, port, q):
         # every rank must hold the full, correctly ordered result == the unsharded run
         want, want_cov, _ = orc.match_batch(hints, pts, offs, nthreads=1)
         ok = bool(np.array_equal(poses.numpy(), want)) and bool(np.array_equal(cov.numpy(), want_cov))
+        # dirty-tile protocol with a host stand-in for the handle (same method names as capi.MapRepB200)
+        import ctypes
+
+        class FakeRep:
+            def __init__(self):
+                self.planes = [np.zeros((32 >> l, 32 >> l), np.float32) for l in range(2)]
+                self.dirty = [None, None]
+
+            def getMapLevels(self):
+                return 2
+
+            def write(self, l, x0, y0, x1, y1, v):
+                self.planes[l][y0:y1 + 1, x0:x1 + 1] = v
+                self.dirty[l] = (x0, y0, x1, y1)
+
+            def get_dirty_rect(self, l, reset=False):
+                r = self.dirty[l]
+                if reset:
+                    self.dirty[l] = None
+                return r
+
+            def _view(self, ptr, n):
+                return np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr))
+
+            def pack_rect_device(self, l, rect, ptr, stream=0):
+                x0, y0, x1, y1 = rect
+                self._view(ptr, (x1 - x0 + 1) * (y1 - y0 + 1))[:] = self.planes[l][y0:y1 + 1, x0:x1 + 1].reshape(-1)
+
+            def unpack_rect_device(self, l, rect, ptr, stream=0):
+                x0, y0, x1, y1 = rect
+                n = (x1 - x0 + 1) * (y1 - y0 + 1)
+                self.planes[l][y0:y1 + 1, x0:x1 + 1] = self._view(ptr, n).reshape(y1 - y0 + 1, x1 - x0 + 1)
+
+        fr = FakeRep()
+        if rank == 0:
+            fr.write(0, 3, 4, 10, 9, 1.5)      # level 1 stays clean on purpose
+        shipped = parallel.broadcast_dirty_tiles(fr, "cpu", src=0)
+        ok = ok and shipped == 8 * 6 and float(fr.planes[0].sum()) == 1.5 * 48 and float(fr.planes[1].sum()) == 0.0
+        ok = ok and fr.get_dirty_rect(0) is None
         lo, hi = parallel.shard_range(K, rank, world)
         q.put((rank, ok, (lo, hi)))
     finally:
