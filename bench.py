@@ -144,7 +144,7 @@ def cpu_reference_run(world, pts, offs, hints, planes, steps: int, warmup: int, 
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=True, capture_output=True)
     kind = "reference" if pyoracle.available("reference") else "port"
     cores = os.cpu_count() or 1
-    threads = max(1, min(cores, 64))
+    threads = max(1, min(cores, 256))
     orc = pyoracle.Oracle(kind, RES, MAP_SIZE, LEVELS)
     orc.set_update_factors(0.4, 0.9)
     for l in range(LEVELS):
