@@ -24,6 +24,10 @@ HOST_LIB = os.path.join(LIBDIR, "libhsb200_host.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
+    # no implicit FMA contraction anywhere (nvcc AND ptxas): the map-coordinate arithmetic must round
+    # like the reference's; ptxas would otherwise fuse even mul.rn.f32x2 + add.rn.f32x2 into FFMA2.
+    # Fused operations are written explicitly (fmaf / __ffma2_rn) where they are wanted.
+    "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "static",
 ]

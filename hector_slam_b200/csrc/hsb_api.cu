@@ -64,7 +64,7 @@ struct hsb_handle {
   // pinned host scratch
   float* h_pin = nullptr;  // 64 floats
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0;
   uint64_t launches = 0;
   std::string err;
 };
@@ -189,7 +189,7 @@ void fill_level_dev(const hsb_handle* h, int l, HsbLevelDev& d) {
 }
 
 // ---- match launch -----------------------------------------------------------------------------
-template <int W, int G, int MODE, int U>
+template <int W, int G, int MODE, int U, bool PACK>
 int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   size_t header = hsb::MatchSmem<W, G>::kHeaderBytes;
   int cap = 0;
@@ -200,7 +200,7 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
   if (P.ranges && cap == 0) return fail(h, HSB_ERR_UNSUPPORTED, "scan too long for the fused range conversion (%d beams)", max_n);
   P.pts_cap = cap;
   size_t smem = header + (size_t)G * cap * 8;
-  auto kern = hsb::match_kernel<W, G, MODE, U>;
+  auto kern = hsb::match_kernel<W, G, MODE, U, PACK>;
   if (smem > 48 * 1024) {
     HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -237,8 +237,11 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
 
 template <int MODE>
 int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int W, int G, int U) {
-#define HSB_CASE(w, g, u) \
-  if (W == w && G == g && U == u) return launch_match_t<w, g, MODE, u>(h, P, max_n, st)
+#define HSB_CASE(w, g, u)                                                                          \
+  if (W == w && G == g && U == u) {                                                                \
+    if (MODE == hsb::MODE_TEX && h->tune_packed) return launch_match_t<w, g, hsb::MODE_TEX, u, true>(h, P, max_n, st); \
+    return launch_match_t<w, g, MODE, u, false>(h, P, max_n, st);                                  \
+  }
   HSB_CASE(1, 1, 4);
   HSB_CASE(1, 2, 4);
   HSB_CASE(1, 4, 4);
@@ -293,6 +296,7 @@ int pipeline_chunk(int B) {
 void fill_match_params(const hsb_handle* h, HsbMatchParams& P) {
   memset(&P, 0, sizeof(P));
   P.levels = h->levels;
+  P.neg_zero = -0.0f;
   for (int l = 0; l < h->levels; ++l) fill_level_dev(h, l, P.lv[l]);
 }
 
@@ -512,6 +516,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "stage_smem")) h->tune_stage_smem = value;
   else if (!strcmp(key, "chunk")) h->tune_chunk = value;
   else if (!strcmp(key, "unroll")) h->tune_unroll = value;
+  else if (!strcmp(key, "packed")) h->tune_packed = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }

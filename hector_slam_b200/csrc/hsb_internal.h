@@ -39,7 +39,7 @@ struct HsbMatchParams {
   int n_beams;
   float range_min, range_max_c;  // keep range_min < r < range_max - 0.1
   float scale_to_map;
-  int* cnt_scratch;         // unused (reserved)
+  float neg_zero;           // -0.0f, deliberately opaque to the compiler (see mul2_exact in match_kernel.cuh)
 };
 
 struct HsbUpdateLevelDev {

@@ -210,17 +210,17 @@ __device__ __forceinline__ void point_accumulate(const PointPre& p, const float4
   const float m = fmaf(fy, fmaf(fx, dd, d02), fmaf(fx, d01, i0));
 #endif
   const float f = 1.0f - m;
-  const float r = p.rx * gy - p.ry * gx;
-  if (p.inside) {
-    a.d0 += gx * f;
-    a.d1 += gy * f;
-    a.d2 += r * f;
-    a.h00 += gx * gx;
-    a.h11 += gy * gy;
-    a.h22 += r * r;
-    a.h01 += gx * gy;
-    a.h02 += gx * r;
-    a.h12 += gy * r;
+  const float r = fmaf(p.rx, gy, -(p.ry * gx));
+  if (p.inside) {  // the translation unit is built with -fmad=false: fused operations are explicit
+    a.d0 = fmaf(gx, f, a.d0);
+    a.d1 = fmaf(gy, f, a.d1);
+    a.d2 = fmaf(r, f, a.d2);
+    a.h00 = fmaf(gx, gx, a.h00);
+    a.h11 = fmaf(gy, gy, a.h11);
+    a.h22 = fmaf(r, r, a.h22);
+    a.h01 = fmaf(gx, gy, a.h01);
+    a.h02 = fmaf(gx, r, a.h02);
+    a.h12 = fmaf(gy, r, a.h12);
   }
 #endif
 }
@@ -260,6 +260,121 @@ __device__ __forceinline__ void eval_points(const LevelRegs& L, PtsPtr pts, int 
 #pragma unroll
     for (int u = 0; u < U; ++u) point_accumulate(pre[u], v[u], a);
   }
+}
+
+// ---- packed (f32x2) evaluation: two endpoints per lane in the two halves of 64-bit registers ----
+// Blackwell's FMA pipe executes add/mul/fma .f32x2 (SASS FADD2 / FMUL2 / FFMA2): one issue slot
+// for two IEEE-rounded fp32 results.  This kernel is bound by instruction issue, not by the FMA
+// pipe (profiles/), so everything of the per-endpoint arithmetic that has the same shape for two
+// endpoints is done pairwise: the exact map-coordinate sequence (4 FMUL2 + 6 FADD2/FFMA2), the
+// interpolation weights, rotDeriv and the nine H / dTr accumulations.  Each half performs exactly
+// the operation sequence of the scalar path, so results per endpoint are bit-identical.
+//
+// Shared-memory layout for this path ("pairified" in place after staging): slots 2k and 2k+1 are
+// stored as (x_2k, x_2k+1, y_2k, y_2k+1), so one LDS.128 delivers the X pair and the Y pair in
+// adjacent registers.  Slots that hold no endpoint, and endpoints that are not finite, are set to
+// kFar: such a point lies outside every map, its texture coordinates are redirected to (-8,-8) where
+// clamp addressing returns four equal texels, hence zero gradient, hence zero contribution —
+// no per-endpoint branch and no predication in the accumulation.
+constexpr float kFar = 1.0e30f;
+
+// Exactly-rounded packed products.  ptxas 12.9 fuses a packed multiply with a following packed add
+// into FFMA2 even when both carry .rn and the build uses -fmad=false (it honours that for scalar
+// code only — checked in isolation), which would change the rounding of the map
+// coordinate.  A product written as fma(a, b, nz) with nz = -0.0f read from a kernel parameter
+// (so the compiler cannot prove it is zero) is bit-identical to round(a*b) — adding -0 preserves
+// value and sign of zero — and an fma feeding an add cannot be contracted any further.
+__device__ __forceinline__ float2 mul2_exact(float2 a, float2 b, float2 nz) { return __ffma2_rn(a, b, nz); }
+__device__ __forceinline__ float2 add2_exact(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// c - a  ==  fma(a, -1, c): one rounding, like the scalar subtraction
+__device__ __forceinline__ float2 sub2_exact(float2 c, float2 a) { return __ffma2_rn(a, make_float2(-1.0f, -1.0f), c); }
+
+template <int W>
+__device__ __forceinline__ void pairify_in_place(float2* slots, int head, int n, int t) {
+  const int nslots = (head + n + 1) & ~1;
+  float4* q = reinterpret_cast<float4*>(slots);
+  for (int k = t; k < nslots / 2; k += W * 32) {
+    float4 v = q[k];  // (x0, y0, x1, y1)
+    const int s0 = 2 * k, s1 = 2 * k + 1;
+    const bool ok0 = (s0 >= head) && (s0 < head + n) && (fabsf(v.x) < kFar) && (fabsf(v.y) < kFar);
+    const bool ok1 = (s1 >= head) && (s1 < head + n) && (fabsf(v.z) < kFar) && (fabsf(v.w) < kFar);
+    const float x0 = ok0 ? v.x : kFar, y0 = ok0 ? v.y : kFar;
+    const float x1 = ok1 ? v.z : kFar, y1 = ok1 ? v.w : kFar;
+    q[k] = make_float4(x0, x1, y0, y1);
+  }
+}
+
+struct Acc2 {
+  float2 h00, h11, h22, h01, h02, h12, d0, d1, d2;
+};
+
+template <int UP>
+__device__ __forceinline__ void eval_pairs(const LevelRegs& L, const float4* __restrict__ pairs, int first, int stride,
+                                           int npairs, float cs, float ss, float x, float y, float neg_zero, Acc& out) {
+  const float2 cs2 = make_float2(cs, cs), ss2 = make_float2(ss, ss), x2 = make_float2(x, x), y2 = make_float2(y, y);
+  const float2 neg1 = make_float2(-1.0f, -1.0f), far4 = make_float2(kFar, kFar);
+  const float2 z = make_float2(0.f, 0.f), nz = make_float2(neg_zero, neg_zero);
+  Acc2 a = {z, z, z, z, z, z, z, z, z};
+  for (int base = first; base < npairs; base += UP * stride) {
+    float2 RX[UP], RY[UP], FX[UP], FY[UP];
+    float4 va[UP], vb[UP];
+#pragma unroll
+    for (int u = 0; u < UP; ++u) {
+      const int k = base + u * stride;
+      float2 X = far4, Y = far4;
+      if (k < npairs) {
+        const float4 v = pairs[k];
+        X = make_float2(v.x, v.y);
+        Y = make_float2(v.z, v.w);
+      }
+      // q = T * p in the oracle's exact order, pairwise (cs/ss carry the level's 2^-k scale)
+      const float2 M1 = mul2_exact(cs2, X, nz), M2 = mul2_exact(ss2, Y, nz), M3 = mul2_exact(ss2, X, nz),
+                   M4 = mul2_exact(cs2, Y, nz);
+      const float2 QX = add2_exact(M1, sub2_exact(x2, M2));         // m1 + (-m2 + x)     OccGridMapUtil.h:80
+      const float2 QY = add2_exact(M3, add2_exact(M4, y2));         // m3 + (m4 + y)
+      RX[u] = sub2_exact(M1, M2);                                   // m1 - m2            (:87)
+      RY[u] = add2_exact(M3, M4);
+      const bool inA = (QX.x >= 0.0f) && (QX.x <= L.lim_x) && (QY.x >= 0.0f) && (QY.x <= L.lim_y);
+      const bool inB = (QX.y >= 0.0f) && (QX.y <= L.lim_x) && (QY.y >= 0.0f) && (QY.y <= L.lim_y);
+      const float2 FLX = make_float2(truncf(QX.x), truncf(QX.y));   // :295
+      const float2 FLY = make_float2(truncf(QY.x), truncf(QY.y));
+      FX[u] = sub2_exact(QX, FLX);                                  // q - floor(q)       (:298)
+      FY[u] = sub2_exact(QY, FLY);
+      // texel centres (ix,iy)..(ix+1,iy+1); outside endpoints look at the clamped corner (4 equal texels)
+      const float cxA = inA ? FLX.x + 1.0f : -8.0f, cyA = inA ? FLY.x + 1.0f : -8.0f;
+      const float cxB = inB ? FLX.y + 1.0f : -8.0f, cyB = inB ? FLY.y + 1.0f : -8.0f;
+      const float4 gA = tex2Dgather<float4>(L.tex, cxA, cyA, 0);
+      const float4 gB = tex2Dgather<float4>(L.tex, cxB, cyB, 0);
+      va[u] = make_float4(gA.w, gA.z, gA.x, gA.y);                  // (i0, i1, i2, i3)
+      vb[u] = make_float4(gB.w, gB.z, gB.x, gB.y);
+    }
+#pragma unroll
+    for (int u = 0; u < UP; ++u) {
+      // regrouped bilinear form (HSB_FP_VARIANT 2), per endpoint; results land pairwise
+      const float d01a = va[u].y - va[u].x, d02a = va[u].z - va[u].x, dda = (va[u].w - va[u].z) - d01a;
+      const float d01b = vb[u].y - vb[u].x, d02b = vb[u].z - vb[u].x, ddb = (vb[u].w - vb[u].z) - d01b;
+      const float2 D01 = make_float2(d01a, d01b), D02 = make_float2(d02a, d02b), DD = make_float2(dda, ddb);
+      const float2 I0 = make_float2(va[u].x, vb[u].x);
+      const float2 GX = __ffma2_rn(FX[u], DD, D01);                 // :344
+      const float2 GY = __ffma2_rn(FY[u], DD, D02);                 // :345
+      const float2 Mv = __ffma2_rn(FY[u], __ffma2_rn(FX[u], DD, D02), __ffma2_rn(FX[u], D01, I0));  // :342-343
+      const float2 F = __ffma2_rn(Mv, neg1, make_float2(1.0f, 1.0f));  // 1 - M            (:82)
+      const float2 T = __fmul2_rn(RY[u], GX);
+      const float2 R = __ffma2_rn(RX[u], GY, make_float2(-T.x, -T.y));  // rx*gy - ry*gx   (:87)
+      a.d0 = __ffma2_rn(GX, F, a.d0);
+      a.d1 = __ffma2_rn(GY, F, a.d1);
+      a.d2 = __ffma2_rn(R, F, a.d2);
+      a.h00 = __ffma2_rn(GX, GX, a.h00);
+      a.h11 = __ffma2_rn(GY, GY, a.h11);
+      a.h22 = __ffma2_rn(R, R, a.h22);
+      a.h01 = __ffma2_rn(GX, GY, a.h01);
+      a.h02 = __ffma2_rn(GX, R, a.h02);
+      a.h12 = __ffma2_rn(GY, R, a.h12);
+    }
+  }
+  out.h00 = a.h00.x + a.h00.y; out.h11 = a.h11.x + a.h11.y; out.h22 = a.h22.x + a.h22.y;
+  out.h01 = a.h01.x + a.h01.y; out.h02 = a.h02.x + a.h02.y; out.h12 = a.h12.x + a.h12.y;
+  out.d0 = a.d0.x + a.d0.y;    out.d1 = a.d1.x + a.d1.y;    out.d2 = a.d2.x + a.d2.y;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -387,7 +502,7 @@ struct MatchSmem {
   static constexpr int kHeaderBytes = ((G * 8 + kRedFloats * 4 + kCntInts * 4) + 15) / 16 * 16;
 };
 
-template <int W, int G, int MODE, int U>
+template <int W, int G, int MODE, int U, bool PACK>
 __global__ void __launch_bounds__(W * G * 32)
     match_kernel(const __grid_constant__ HsbMatchParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -456,6 +571,14 @@ __global__ void __launch_bounds__(W * G * 32)
       staged = true;
     }
 
+    int pack_head = 0;
+    if (PACK && staged) {
+      pack_head = (int)(spts_scan - spts);
+      pairify_in_place<W>(spts, pack_head, n, t);
+      group_sync<W>(g);
+    }
+    const int npairs = (pack_head + n + 1) >> 1;
+
     float wx = P.hints[3 * scan + 0], wy = P.hints[3 * scan + 1], wpsi = P.hints[3 * scan + 2];
     Acc last;
     acc_zero(last);
@@ -470,7 +593,9 @@ __global__ void __launch_bounds__(W * G * 32)
           const float cs = cosf_glibc(epsi) * L.pt_scale, ss = sinf_glibc(epsi) * L.pt_scale;
           Acc a;
           acc_zero(a);
-          if (staged)
+          if (PACK && staged)
+            eval_pairs<(U + 1) / 2>(LR, reinterpret_cast<const float4*>(spts), t, GT, npairs, cs, ss, ex, ey, P.neg_zero, a);
+          else if (staged)
             eval_points<MODE, U>(LR, spts_scan, t, GT, n, cs, ss, ex, ey, a);
           else
             eval_points<MODE, U>(LR, gpts, t, GT, n, cs, ss, ex, ey, a);

@@ -147,6 +147,16 @@ def test_match_goldens(hsb_lib, mode, name):
     rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=0)
     P, _ = rep.match_batch(g["hints"], pts, offs)
     check_poses(P, g["ref_poses"], "no smem staging")
+    if mode == 2:
+        # experimental f32x2 (FFMA2/FADD2) evaluation path: same per-endpoint operation sequence,
+        # so the same launch shape must give bit-identical poses
+        for w in (1, 2, 4):
+            rep.set_tuning(warps_per_scan=w, scans_per_block=1, stage_smem=1, packed=0)
+            A, _ = rep.match_batch(g["hints"], pts, offs)
+            rep.set_tuning(packed=1)
+            Bp, _ = rep.match_batch(g["hints"], pts, offs)
+            assert np.array_equal(A, Bp), w
+        rep.set_tuning(packed=0)
     rep.close()
 
 
