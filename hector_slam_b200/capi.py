@@ -27,7 +27,7 @@ EXPORTED = [
     "hsb_refresh_level", "hsb_last_error", "hsb_status_string", "hsb_get_launch_count", "hsb_get_gather_mode",
     "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
     "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch",
-    "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device",
+    "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device", "hsb_raycast_batch",
 ]
 
 
@@ -115,6 +115,7 @@ def load_library() -> C.CDLL:
     sig("hsb_download_occupancy", i, vp, i, vp)
     sig("hsb_likelihood_batch", i, vp, i, i, vp, vp, vp, i, vp)
     sig("hsb_get_dirty_rect", i, vp, i, vp, i)
+    sig("hsb_raycast_batch", i, vp, i, i, vp, vp, vp, vp)
     sig("hsb_pack_rect_device", i, vp, i, vp, vp, vp)
     sig("hsb_unpack_rect_device", i, vp, i, vp, vp, vp)
     _lib = L
@@ -378,6 +379,17 @@ class MapRepB200:
         self._check(self.lib.hsb_likelihood_batch(self.h, level, B, poses.ctypes.data, pts.ctypes.data if pts.size else None,
                                                   offp, n_shared, out.ctypes.data))
         return out
+
+    def raycast_batch(self, level: int, begin_cells, end_cells):
+        """checkOccupancyBresenhami for B rays. -> (dist (B,) float32 [-1 = no hit], hit (B,2) int32)"""
+        b = np.ascontiguousarray(begin_cells, dtype=np.int32).reshape(-1, 2)
+        e = np.ascontiguousarray(end_cells, dtype=np.int32).reshape(-1, 2)
+        B = b.shape[0]
+        dist = np.zeros(B, np.float32)
+        hit = np.zeros((B, 2), np.int32)
+        self._check(self.lib.hsb_raycast_batch(self.h, level, B, b.ctypes.data, e.ctypes.data, dist.ctypes.data,
+                                               hit.ctypes.data))
+        return dist, hit
 
     def get_dirty_rect(self, level: int, reset: bool = False):
         """(x0, y0, x1, y1) inclusive of the cells written since the last reset, or None."""

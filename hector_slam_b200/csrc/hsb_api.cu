@@ -1057,6 +1057,32 @@ int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const fl
   return HSB_OK;
 }
 
+int hsb_raycast_batch(hsb_handle* h, int level, int B, const int* begin_cells, const int* end_cells, float* out_dist,
+                      int* out_hit) {
+  if (!h || level < 0 || level >= h->levels || B < 0 || !begin_cells || !end_cells || !out_dist) return HSB_ERR_INVALID_ARG;
+  if (B == 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  int s;
+  if ((s = ensure(h, h->d_pts, (size_t)B * 16 + 16)) != HSB_OK) return s;      // begin | end
+  if ((s = ensure(h, h->d_poses, (size_t)B * 12 + 16)) != HSB_OK) return s;    // dist | hit
+  cudaStream_t st = h->stream;
+  int2* d_begin = static_cast<int2*>(h->d_pts.p);
+  int2* d_end = d_begin + B;
+  float* d_dist = static_cast<float*>(h->d_poses.p);
+  int2* d_hit = reinterpret_cast<int2*>(d_dist + ((B + 1) & ~1));
+  HSB_CUDA(h, cudaMemcpyAsync(d_begin, begin_cells, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  HSB_CUDA(h, cudaMemcpyAsync(d_end, end_cells, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  int blocks = std::min((B + 7) / 8, h->sm_count * 8);
+  hsb::raycast_kernel<<<blocks, 256, 0, st>>>(L.logodds, L.sx, L.sy, B, d_begin, d_end, d_dist, out_hit ? d_hit : nullptr);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  HSB_CUDA(h, cudaMemcpyAsync(out_dist, d_dist, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (out_hit) HSB_CUDA(h, cudaMemcpyAsync(out_hit, d_hit, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  return HSB_OK;
+}
+
 void* hsb_level_logodds_device_ptr(hsb_handle* h, int level) {
   if (!h || level < 0 || level >= h->levels) return nullptr;
   return h->lv[level].logodds;

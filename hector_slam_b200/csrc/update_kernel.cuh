@@ -73,6 +73,57 @@ __global__ void occupancy_kernel(const float* __restrict__ logodds, int8_t* __re
   }
 }
 
+// N4: DistanceMeasurementProvider::checkOccupancyBresenhami (HectorMapTools.h:133-216), one warp per ray.
+// Same closed-form line as K2; 32 cells are tested per step and the first occupied one wins.
+__global__ void __launch_bounds__(256)
+    raycast_kernel(const float* __restrict__ logodds, int sx, int sy, int B, const int2* __restrict__ begin,
+                   const int2* __restrict__ end, float* __restrict__ out_dist, int2* __restrict__ out_hit) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b < B; b += nwarps) {
+    const int2 p0 = begin[b], p1 = end[b];
+    float dist = -1.0f;
+    int2 hit = make_int2(-1, -1);
+    const bool ok = p0.x >= 0 && p0.x < sx && p0.y >= 0 && p0.y < sy && p1.x >= 0 && p1.x < sx && p1.y >= 0 && p1.y < sy;  // :141-154
+    if (ok) {
+      const int dx = p1.x - p0.x, dy = p1.y - p0.y;
+      const unsigned adx = (unsigned)abs(dx), ady = (unsigned)abs(dy);
+      const int off_dx = dx > 0 ? 1 : -1, off_dy = (dy > 0 ? 1 : -1) * sx;   // :162-163
+      unsigned ada, adb;
+      int off_a, off_b;
+      if (adx >= ady) { ada = adx; adb = ady; off_a = off_dx; off_b = off_dy; }   // :170-177
+      else            { ada = ady; adb = adx; off_a = off_dy; off_b = off_dx; }
+      const unsigned err0 = ada / 2u;
+      const unsigned start = (unsigned)p0.y * (unsigned)sx + (unsigned)p0.x;
+      const unsigned steps = min(5000u, ada);                                    // :203
+      for (unsigned base = 0; base < steps; base += 32u) {
+        const unsigned i = base + (unsigned)lane;
+        unsigned off = 0;
+        bool occ = false;
+        if (i < steps) {
+          const unsigned carries = (unsigned)(((unsigned long long)err0 + (unsigned long long)i * adb) / ada);
+          off = start + (unsigned)((int)i * off_a) + (unsigned)((int)carries * off_b);
+          occ = logodds[off] > 0.0f;                                             // data[offset] == 100  (:208)
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, occ);
+        if (m) {
+          const int first = __ffs(m) - 1;
+          const unsigned hoff = __shfl_sync(0xffffffffu, off, first);
+          hit = make_int2((int)(hoff % (unsigned)sx), (int)(hoff / (unsigned)sx));   // :182
+          const float fx = (float)(p0.x - hit.x), fy = (float)(p0.y - hit.y);
+          dist = (float)(int)__fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));  // int distMap = norm  (:184)
+          break;
+        }
+      }
+    }
+    if (lane == 0) {
+      out_dist[b] = dist;
+      if (out_hit) out_hit[b] = hit;
+    }
+  }
+}
+
 __device__ __forceinline__ void claim_and_apply(const HsbUpdateLevelDev& L, unsigned off, float lf, float lo) {
   const uint32_t base = L.stamp_base;
   const uint32_t v = __ldcg(L.stamp + off);

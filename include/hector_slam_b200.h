@@ -215,6 +215,16 @@ int hsb_download_occupancy(hsb_handle* h, int level, int8_t* occupancy_host_out)
 int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses_world, const float* points_xy,
                          const int* offsets, int n_shared, float* out_likelihood);
 
+/* hector_map_tools' DistanceMeasurementProvider::checkOccupancyBresenhami
+ * (hector_map_tools/include/hector_map_tools/HectorMapTools.h:133-216, bresenham2D :200-216), B rays
+ * at once on one level: walk the Bresenham line from begin cell to end cell (start included, end
+ * excluded, at most 5000 steps) and stop at the first OCCUPIED cell (occupancy value 100, i.e.
+ * log-odds > 0).  out_dist[b] = (int) Euclidean distance begin -> hit in cells, as a float, or -1
+ * if nothing is hit or begin / end lies outside the level; out_hit (may be NULL) receives the hit
+ * cell (x, y) or (-1, -1).  begin_cells / end_cells: B x 2 int32 (x, y).  Host buffers. */
+int hsb_raycast_batch(hsb_handle* h, int level, int B, const int* begin_cells, const int* end_cells, float* out_dist,
+                      int* out_hit);
+
 /* ---- diagnostics ----------------------------------------------------------------------------*/
 const char* hsb_last_error(const hsb_handle* h);
 const char* hsb_status_string(int status);

@@ -679,6 +679,53 @@ float hso_likelihood(void* hv, int level, const float pose_map[3], const float* 
   return 1 - (residual / sizef);
 }
 
+/* hector_map_tools DistanceMeasurementProvider::checkOccupancyBresenhami + bresenham2D
+ * (/root/reference/hector_map_tools/include/hector_map_tools/HectorMapTools.h:133-216), on a level's
+ * log-odds plane: a cell's nav_msgs value is 100 iff its log-odds is > 0 (HectorMappingRos.cpp:462-465).
+ * (The header needs nav_msgs / ROS and cannot be compiled here: pinned by restatement only.) */
+float hso_raycast(void* hv, int level, int x0, int y0, int x1, int y1, int hit[2]) {
+  level_t* L = &((hso_t*)hv)->lv[level];
+  int size_x = L->size_x, size_y = L->size_y;
+  hit[0] = hit[1] = -1;
+  if ((x0 < 0) || (x0 >= size_x) || (y0 < 0) || (y0 >= size_y)) return -1.0f; /* :141 */
+  if ((x1 < 0) || (x1 >= size_x) || (y1 < 0) || (y1 >= size_y)) return -1.0f; /* :152 */
+  int dx = x1 - x0, dy = y1 - y0;
+  unsigned int abs_dx = abs(dx), abs_dy = abs(dy);
+  int offset_dx = dx > 0 ? 1 : -1;
+  int offset_dy = (dy > 0 ? 1 : -1) * size_x;
+  unsigned int offset = y0 * size_x + x0;
+  unsigned int abs_da, abs_db;
+  int error_b, offset_a, offset_b;
+  if (abs_dx >= abs_dy) { /* :170 */
+    abs_da = abs_dx; abs_db = abs_dy; error_b = abs_dx / 2; offset_a = offset_dx; offset_b = offset_dy;
+  } else {
+    abs_da = abs_dy; abs_db = abs_dx; error_b = abs_dy / 2; offset_a = offset_dy; offset_b = offset_dx;
+  }
+  unsigned int end = abs_da < 5000u ? abs_da : 5000u; /* :203 std::min(max_length, abs_da) */
+  int end_offset = -1;
+  for (unsigned int i = 0; i < end; ++i) { /* :207-216 */
+    if (L->logodds[offset] > 0.0f) {
+      end_offset = (int)offset;
+      break;
+    }
+    offset += offset_a;
+    error_b += abs_db;
+    if ((unsigned int)error_b >= abs_da) {
+      offset += offset_b;
+      error_b -= abs_da;
+    }
+  }
+  if (end_offset != -1) {
+    int ex = end_offset % size_x, ey = end_offset / size_x; /* :182 */
+    float fx = (float)(x0 - ex), fy = (float)(y0 - ey);
+    int dist_map = (int)sqrtf(fx * fx + fy * fy); /* :184 */
+    hit[0] = ex;
+    hit[1] = ey;
+    return (float)dist_map;
+  }
+  return -1.0f;
+}
+
 /* HectorMappingRos::rosLaserScanToDataContainer — hector_mapping/src/HectorMappingRos.cpp:483-507.
  * (That file needs ROS and cannot be compiled here, so this row of the path is pinned by this
  * restatement only.)  `cos(angle)` / `sin(angle)` are called on a float with the <cmath> overloads

@@ -185,6 +185,15 @@ class Oracle:
         self._fn("hessian_derivs")(self.h, level, _f32(pose_map), pts, pts.shape[0], H, d)
         return H.reshape(3, 3), d
 
+    def raycast(self, level: int, begin, end):
+        """checkOccupancyBresenhami (port only). -> (dist, (hx, hy))"""
+        fn = self.lib.hso_raycast
+        fn.restype = C.c_float
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        hit = (C.c_int * 2)()
+        d = fn(self.h, level, int(begin[0]), int(begin[1]), int(end[0]), int(end[1]), hit)
+        return float(d), (int(hit[0]), int(hit[1]))
+
     def likelihood(self, level: int, pose_map, pts_level) -> float:
         """OccGridMapUtil::getLikelihoodForState (state and points in the level's cell units)."""
         pts = _f32(pts_level).reshape(-1, 2)

@@ -93,3 +93,34 @@ def test_config4_best_hypothesis_by_likelihood(hsb_lib, pyoracle):
     assert np.abs(best[:2] - truth[:2]).max() < 0.02
     rep.close()
     orc.close()
+
+
+def test_raycast_batch_bit_exact(hsb_lib, pyoracle):
+    """N4: hector_map_tools' checkOccupancyBresenhami, 20 000 rays at once, against the C restatement
+    (integer work: distances, hit cells and misses must be identical)."""
+    from hector_slam_b200 import capi
+
+    g = load_golden("match3.npz")
+    size = int(g["size"])
+    rep = capi.MapRepB200(float(g["res"]), size, levels=3)
+    orc = pyoracle.Oracle("port", float(g["res"]), size, 3)
+    for l, p in enumerate(golden_planes(g)):
+        rep.upload_level(l, p)
+        orc.set_logodds(l, p)
+    rng = np.random.default_rng(4)
+    for level in (0, 2):
+        s = size >> level
+        B = 20000 if level == 0 else 2000
+        begin = rng.integers(int(0.3 * s), int(0.7 * s), (B, 2)).astype(np.int32)     # mostly inside the room
+        end = rng.integers(-5, s + 5, (B, 2)).astype(np.int32)                       # some outside the map
+        begin[:50] = rng.integers(-3, s + 3, (50, 2))                                  # some starts outside too
+        end[50:60] = begin[50:60]                                                      # zero-length rays
+        dist, hit = rep.raycast_batch(level, begin, end)
+        n_hit = 0
+        for b in range(0, B, 7 if level == 0 else 1):
+            d, h = orc.raycast(level, begin[b], end[b])
+            assert dist[b] == d and tuple(hit[b]) == h, (level, b, dist[b], d, hit[b], h)
+            n_hit += d >= 0
+        assert n_hit > 100
+    rep.close()
+    orc.close()
