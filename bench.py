@@ -288,7 +288,8 @@ def main():
                 r2.upload_level(l, planes_host[l])
             for (w, g, stage, unroll) in combos:
                 if True:
-                    r2.set_tuning(warps_per_scan=w, scans_per_block=g, stage_smem=stage, unroll=unroll)
+                    r2.set_tuning(warps_per_scan=w, scans_per_block=g, stage_smem=stage, unroll=unroll,
+                                  packed=int(os.environ.get("HSB_PACKED", "0")), seq=int(os.environ.get("HSB_SEQ", "0")))
                     for i in range(min(3, args.sweep_iters)):
                         r2.match_batch_device(B, d_hints[0].data_ptr(), d_pts[0].data_ptr(), d_offs.data_ptr(), 0, N_PTS,
                                               d_poses.data_ptr(), d_cov.data_ptr(), stream)

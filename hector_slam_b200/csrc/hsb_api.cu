@@ -64,7 +64,7 @@ struct hsb_handle {
   // pinned host scratch
   float* h_pin = nullptr;  // 64 floats
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0;
   uint64_t launches = 0;
   std::string err;
 };
@@ -192,34 +192,48 @@ void fill_level_dev(const hsb_handle* h, int l, HsbLevelDev& d) {
 template <int W, int G, int MODE, int U, bool PACK>
 int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   size_t header = hsb::MatchSmem<W, G>::kHeaderBytes;
+  auto kern = hsb::match_kernel<W, G, MODE, U, PACK>;
   int cap = 0;
   if (h->tune_stage_smem || P.ranges) {
     cap = ((max_n + 1) + 1) & ~1;  // n + head padding, even
     if (header + (size_t)G * cap * 8 > 200 * 1024) cap = 0;
   }
   if (P.ranges && cap == 0) return fail(h, HSB_ERR_UNSUPPORTED, "scan too long for the fused range conversion (%d beams)", max_n);
+  // resident CTAs per SM for a given dynamic shared-memory size: block, thread, register and
+  // shared-memory limits (1 KB per CTA is reserved by the driver)
+  static int regs = 0;
+  if (!regs) {
+    cudaFuncAttributes fa;
+    HSB_CUDA(h, cudaFuncGetAttributes(&fa, kern));
+    regs = fa.numRegs > 0 ? fa.numRegs : 32;
+  }
+  const int threads = W * G * 32;
+  auto resident = [&](size_t smem_bytes) {
+    int blocks = std::min(32, 2048 / threads);
+    blocks = std::min(blocks, 65536 / (((regs + 7) / 8 * 8) * threads));
+    blocks = std::min<long>(blocks, (long)(232448 / (smem_bytes + 1024)));
+    return std::max(blocks, 1);
+  };
+  if (cap > 0 && !P.ranges && h->tune_stage_smem == 1) {
+    // Wave quantisation (profiles/r01_sweep_large_batches.log): staging costs ~9 KB of shared memory
+    // per scan, i.e. fewer resident groups.  If the batch does not fit the resident groups WITH
+    // staging but does fit WITHOUT (one wave instead of one and a bit), read the endpoints through
+    // L1 instead — measured 28.5 vs 24.5 M matches/s at B = 4096.
+    const long groups = ((long)P.B + G - 1) / G;
+    const long slots_staged = (long)resident(header + (size_t)G * cap * 8) * h->sm_count;
+    const long slots_plain = (long)resident(header) * h->sm_count;
+    if (groups > slots_staged && groups <= slots_plain) cap = 0;
+  }
   P.pts_cap = cap;
   size_t smem = header + (size_t)G * cap * 8;
-  auto kern = hsb::match_kernel<W, G, MODE, U, PACK>;
   if (smem > 48 * 1024) {
     HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   {
     // Shared-memory carve-out: left alone the driver picks a small one for kernels that ask for a
     // few hundred bytes, which then caps resident CTAs (measured: 7 CTAs/SM for 64-thread blocks).
-    // Ask for what full occupancy of this launch shape needs.
-    static int regs = 0;
-    if (!regs) {
-      cudaFuncAttributes fa;
-      HSB_CUDA(h, cudaFuncGetAttributes(&fa, kern));
-      regs = fa.numRegs > 0 ? fa.numRegs : 32;
-    }
-    const int threads = W * G * 32;
-    int blocks = 2048 / threads;
-    blocks = std::min(blocks, 32);
-    blocks = std::min(blocks, 65536 / (((regs + 7) / 8 * 8) * threads));
-    blocks = std::max(blocks, 1);
-    size_t need = (size_t)blocks * (smem + 1024);
+    // Ask for what full occupancy of this launch shape needs, no more (the rest stays L1).
+    size_t need = (size_t)resident(smem) * (smem + 1024);
     int pct = (int)((need * 100 + 233471) / 233472);
     pct = std::min(100, std::max(pct, 4));
     static int last_pct = -1;
@@ -228,7 +242,8 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
       last_pct = pct;
     }
   }
-  int grid = (P.B + G - 1) / G;
+  const int seq = h->tune_seq > 0 ? h->tune_seq : 1;  // scans each group handles one after the other
+  int grid = (P.B + G * seq - 1) / (G * seq);
   kern<<<grid, W * G * 32, smem, st>>>(P);
   h->launches++;
   HSB_CUDA(h, cudaGetLastError());
@@ -269,13 +284,13 @@ int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t 
 int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   int W = h->tune_warps_per_scan, G = h->tune_scans_per_block;
   if (W <= 0) {
-    // Measured on B200 (profiles/r01_sweep_batches.log): one or two warps per scan once the batch
-    // fills the chip, more warps per scan for small batches, never more than 8 (the per-evaluation
-    // reduction / barrier cost grows with the group size).
+    // Measured on B200 (profiles/r01_sweep_batches.log, r01_sweep_large_batches.log): one warp per
+    // scan as soon as the batch fills the chip (best at every B >= 2048, 34 M matches/s at 65536),
+    // more warps per scan for small batches, never more than 8 (the per-evaluation reduction /
+    // barrier cost grows with the group size).
     long want = ((long)h->sm_count * 24) / (P.B > 0 ? P.B : 1);
     W = 1;
     while (W * 2 <= want && W < 8) W *= 2;
-    if (P.B >= 3072) W = 2;
   }
   if (G <= 0) G = 1;
   int U = h->tune_unroll > 0 ? h->tune_unroll : 4;
@@ -517,6 +532,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "chunk")) h->tune_chunk = value;
   else if (!strcmp(key, "unroll")) h->tune_unroll = value;
   else if (!strcmp(key, "packed")) h->tune_packed = value;
+  else if (!strcmp(key, "seq")) h->tune_seq = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }
