@@ -236,11 +236,8 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
     size_t need = (size_t)resident(smem) * (smem + 1024);
     int pct = (int)((need * 100 + 233471) / 233472);
     pct = std::min(100, std::max(pct, 4));
-    static int last_pct = -1;
-    if (pct != last_pct) {
-      HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-      last_pct = pct;
-    }
+    // (function attributes are per device: set on every launch rather than cached per process)
+    HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
   }
   const int seq = h->tune_seq > 0 ? h->tune_seq : 1;  // scans each group handles one after the other
   int grid = (P.B + G * seq - 1) / (G * seq);

@@ -21,7 +21,9 @@
  *   - "host" entry points take host pointers and return when the result is in the output
  *     buffers; "_device" entry points take device pointers and a CUDA stream (cudaStream_t cast
  *     to void*) and are asynchronous on that stream.
- *   - a handle is single-writer, like the reference (one spinner thread calls update()).
+ *   - a handle is single-writer, like the reference (one spinner thread calls update()): calls on
+ *     one handle must not overlap, and work queued by a "_device" entry point on a caller stream
+ *     must have completed (or be ordered by the caller) before a call that writes the map.
  *   - numerical edge cases keep the reference's silent semantics: empty scan -> pose = hint and
  *     the covariance buffer is left untouched (ScanMatcher.h:68,189); H(0,0)==0 or H(1,1)==0 ->
  *     the Gauss-Newton step is skipped (ScanMatcher.h:201); endpoints outside [0, S-2] add

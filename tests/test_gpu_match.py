@@ -262,3 +262,46 @@ def test_batch_parity_against_oracle_2048_three_levels(hsb_lib, pyoracle, oracle
     assert np.abs(got[ok][:, :2] - poses[ok][:, :2]).max() < 0.03  # and close to the ground truth
     rep.close()
     orc.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_non_square_map_other_resolution_and_start(hsb_lib, pyoracle, oracle_kinds, mode):
+    """map_size_x != map_size_y, resolution 0.025 (the node's default), start coords off-centre,
+    two levels: SLAM a few scans on both sides, then batch-match; planes and poses must agree."""
+    from hector_slam_b200 import capi, synth
+
+    kind = "reference" if "reference" in oracle_kinds else "port"
+    res, sx, sy, start = 0.025, 1280, 896, (0.4, 0.55)
+    orc = pyoracle.Oracle(kind, res, sx, 2, start=start, size_y=sy)
+    orc.set_update_factors(0.4, 0.9)
+    rep = capi.MapRepB200(res, sx, sy, levels=2, start=start, update_factor_free=0.4, update_factor_occupied=0.9,
+                          gather_mode=mode)
+    assert rep.level_info(1)[:2] == (640, 448) and orc.level_size(1) == (640, 448)
+    world = synth.World(1, seed=21)
+    rng = np.random.default_rng(3)
+    scale = rep.getScaleToMap()
+    assert scale == np.float32(1.0) / np.float32(res)
+    poses = world.mapping_poses()[:10]
+    for p in poses:
+        scan = synth.make_scan(world, p, rng, scale_to_map=scale)
+        p32 = p.astype(np.float32)
+        orc.match(p32, scan)
+        orc.update_by_scan(scan, p32)
+        orc.on_map_updated()
+        rep.matchData(p32, scan)
+        rep.updateByScan(scan, p32)
+        rep.onMapUpdated()
+    for l in range(2):
+        d = np.abs(rep.download_level(l) - orc.get_logodds(l))
+        assert (d > 1e-5).sum() <= max(3, int(5e-4 * (d.size))), (l, int((d > 1e-5).sum()))
+        rep.upload_level(l, orc.get_logodds(l))      # continue from identical planes
+    test_poses = world.sample_free_poses(64, rng, margin=0.8)
+    pts, offs = synth.make_scan_batch(world, test_poses, noise_seed=5, scale_to_map=scale)
+    hints = synth.perturb_hints(test_poses, seed=6, dxy=0.05, dpsi=0.03)
+    want, _, _ = orc.match_batch(hints, pts, offs)
+    got, _ = rep.match_batch(hints, pts, offs)
+    ok = np.abs(want[:, :2] - hints[:, :2]).max(axis=1) < 0.5
+    assert ok.mean() > 0.9
+    check_poses(got[ok], want[ok], "non-square")
+    rep.close()
+    orc.close()
