@@ -244,6 +244,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world_size > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     gather = {"auto": capi.GATHER_AUTO, "ldg": capi.GATHER_LDG, "tex": capi.GATHER_TEX}[args.gather]
