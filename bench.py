@@ -277,7 +277,7 @@ def main():
                                d_poses.data_ptr(), d_cov.data_ptr(), stream)
 
     if args.sweep:
-        shapes = [(1, 1), (1, 2), (1, 4), (1, 8), (2, 1), (2, 2), (2, 4), (4, 1), (4, 2), (8, 1), (16, 1)]
+        shapes = [(1, 1), (1, 2), (2, 1), (2, 2), (4, 1), (8, 1), (16, 1)]
         combos = [(w, g, st) for st in (1, 0) for (w, g) in shapes]
         if args.shapes:
             combos = [tuple(int(x) for x in c.split(",")) for c in args.shapes.split(";") if c]

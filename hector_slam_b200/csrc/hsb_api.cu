@@ -254,26 +254,19 @@ int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t 
     if (MODE == hsb::MODE_TEX && h->tune_packed) return launch_match_t<w, g, hsb::MODE_TEX, u, true>(h, P, max_n, st); \
     return launch_match_t<w, g, MODE, u, false>(h, P, max_n, st);                                  \
   }
+  // launch shapes kept after the sweeps in profiles/ (groups per CTA > 1 and more than 16 warps
+  // per scan never won anywhere and were dropped)
   HSB_CASE(1, 1, 4);
   HSB_CASE(1, 2, 4);
-  HSB_CASE(1, 4, 4);
-  HSB_CASE(1, 8, 4);
   HSB_CASE(2, 1, 4);
   HSB_CASE(2, 2, 4);
-  HSB_CASE(2, 4, 4);
   HSB_CASE(4, 1, 4);
-  HSB_CASE(4, 2, 4);
   HSB_CASE(8, 1, 4);
   HSB_CASE(16, 1, 4);
-  HSB_CASE(17, 1, 4);
-  HSB_CASE(32, 1, 4);
   // deeper gather batches: the whole per-lane share of a 1081-point scan in flight at once
   HSB_CASE(1, 1, 8);
   HSB_CASE(2, 1, 8);
-  HSB_CASE(4, 1, 8);
-  HSB_CASE(4, 1, 9);
   HSB_CASE(8, 1, 5);
-  HSB_CASE(16, 1, 3);
 #undef HSB_CASE
   return fail(h, HSB_ERR_INVALID_ARG, "unsupported tuning warps_per_scan=%d scans_per_block=%d unroll=%d", W, G, U);
 }
