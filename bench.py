@@ -347,6 +347,8 @@ def main():
     from hector_slam_b200 import synth
 
     rep.set_scan_format(**synth.SCAN_FORMAT)
+    # host buffers local to the GPU's NUMA node (restored before the CPU baseline uses all cores)
+    prev_affinity = parallel.bind_process_to_gpu_numa_node(local_rank)
     h_ranges = torch.from_numpy(np.ascontiguousarray(make_workload.ranges)).pin_memory()
     h_pts = torch.from_numpy(pts).pin_memory()
     h_hints = torch.from_numpy(hints).pin_memory()
@@ -380,6 +382,8 @@ def main():
 
     e2e_xy_value, _ = time_host(step_e2e_xy)
     e2e_value, e2e_launches = time_host(step_e2e)
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)
     clocks = sampler.stop() if rank == 0 else None
 
     # parity spot check of the e2e result against the device-resident path (same inputs)
@@ -407,6 +411,8 @@ def main():
                     "d2h_bytes_per_step": int(B * 12 + B * 36), "launches": int(e2e_launches),
                     "call": "hsb_match_batch_ranges: pinned host sensor ranges (4 B/beam) + hints in, poses + "
                             "covariances out; scan->endpoint conversion fused into the match kernel",
+                    "host_buffers": "pinned, allocated with the process bound to the GPU's NUMA node"
+                                    if prev_affinity is not None else "pinned (NUMA node of the GPU unknown)",
                     "max_abs_diff_vs_device_path": same},
             "e2e_endpoints": {"value": e2e_xy_value, "unit": "scan-matches/s",
                               "h2d_bytes_per_step": int(pts.nbytes + hints.nbytes + offs.nbytes),

@@ -289,13 +289,27 @@ int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G, U);
 }
 
-// Copy/compute pipeline granularity of the host-buffer batch calls.  Chunks must stay large enough
-// for the match kernel to run at full efficiency (>= 1024 scans, profiles/r01_sweep_batches.log) and
-// few enough that the un-overlapped tail (last chunk's kernel) stays small: 4 chunks.
-int pipeline_chunk(int B) {
-  int c = (B + 3) / 4;
-  if (c < 1024) c = 1024;
-  return c < B ? c : B;
+// Copy/compute pipeline of the host-buffer batch calls: chunk c's host->device copy overlaps the
+// match kernel of chunk c-1; only the LAST chunk's kernel is exposed.  So the chunks shrink towards
+// the end (3/8, 3/8, 3/16, 1/16 of the batch): the big early chunks run the kernel at full
+// efficiency (>= 1024 scans, profiles/r01_sweep_batches.log) and the exposed tail is a 1/16 chunk.
+// Returns the chunk boundaries (ascending, first 0, last B).
+std::vector<int> pipeline_bounds(int B, int fixed_chunk) {
+  std::vector<int> b;
+  b.push_back(0);
+  if (fixed_chunk > 0) {
+    for (int x = fixed_chunk; x < B; x += fixed_chunk) b.push_back(x);
+  } else if (B >= 4096) {
+    const int a = (int)((long)B * 3 / 8), c = (int)((long)B * 3 / 16);
+    b.push_back(a);
+    b.push_back(2 * a);
+    b.push_back(2 * a + c);
+  } else if (B >= 2048) {
+    b.push_back(B / 2);
+    b.push_back(B / 2 + B / 4);
+  }
+  b.push_back(B);
+  return b;
 }
 
 void fill_match_params(const hsb_handle* h, HsbMatchParams& P) {
@@ -633,8 +647,8 @@ int hsb_match_batch(hsb_handle* h, int B, const float* hints, const float* pts, 
 
   // Pipeline: the batch is cut into chunks; chunk c's host->device copy runs on copy stream c%2
   // while chunk c-1 is being matched, and results stream back behind each kernel.
-  int chunk = h->tune_chunk > 0 ? h->tune_chunk : pipeline_chunk(B);
-  if (!offsets) chunk = B;  // shared scan: nothing big to overlap
+  std::vector<int> bounds = pipeline_bounds(B, h->tune_chunk);
+  if (!offsets) bounds = std::vector<int>{0, B};  // shared scan: nothing big to overlap
   cudaStream_t s0 = h->copy_stream[0];
   if (offsets) {
     HSB_CUDA(h, cudaMemcpyAsync(d_off, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s0));
@@ -644,9 +658,8 @@ int hsb_match_batch(hsb_handle* h, int B, const float* hints, const float* pts, 
   HSB_CUDA(h, cudaMemcpyAsync(d_hints, hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
   HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
   HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
-  int ci = 0;
-  for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
-    int b1 = b0 + chunk < B ? b0 + chunk : B;
+  for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
+    const int b0 = bounds[ci], b1 = bounds[ci + 1];
     cudaStream_t st = h->copy_stream[ci & 1];
     if (offsets) {
       size_t p0 = (size_t)offsets[b0], p1 = (size_t)offsets[b1];
@@ -784,14 +797,13 @@ int hsb_match_batch_ranges(hsb_handle* h, int B, const float* hints, const float
   float* d_poses = static_cast<float*>(h->d_poses.p);
   float* d_cov = out_cov ? static_cast<float*>(h->d_cov.p) : nullptr;
   // same copy/compute pipeline as hsb_match_batch
-  int chunk = h->tune_chunk > 0 ? h->tune_chunk : pipeline_chunk(B);
+  const std::vector<int> bounds = pipeline_bounds(B, h->tune_chunk);
   cudaStream_t s0 = h->copy_stream[0];
   HSB_CUDA(h, cudaMemcpyAsync(d_hints, hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
   HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
   HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
-  int ci = 0;
-  for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
-    int b1 = b0 + chunk < B ? b0 + chunk : B;
+  for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
+    const int b0 = bounds[ci], b1 = bounds[ci + 1];
     cudaStream_t st = h->copy_stream[ci & 1];
     HSB_CUDA(h, cudaMemcpyAsync(d_ranges + (size_t)b0 * nb, ranges + (size_t)b0 * nb, (size_t)(b1 - b0) * nb * 4,
                                 cudaMemcpyHostToDevice, st));

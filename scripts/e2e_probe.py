@@ -11,6 +11,9 @@ rep = capi.MapRepB200(bench.RES, bench.MAP_SIZE, levels=3, update_factor_free=0.
 world, poses, pts, offs, hints = bench.make_workload(0, B)
 bench.build_map_on_gpu(rep, world)
 rep.set_scan_format(**synth.SCAN_FORMAT)
+from hector_slam_b200 import parallel
+if len(sys.argv) > 1 and sys.argv[1] == "bind":
+    print("affinity before:", len(os.sched_getaffinity(0)), "bound ->", parallel.bind_process_to_gpu_numa_node(0) is not None, len(os.sched_getaffinity(0)))
 h_ranges = torch.from_numpy(np.ascontiguousarray(bench.make_workload.ranges)).pin_memory()
 h_pts = torch.from_numpy(pts).pin_memory()
 h_hints = torch.from_numpy(hints).pin_memory()
