@@ -2,6 +2,7 @@
 // kernels in match_kernel.cuh / update_kernel.cuh.  No torch types, no CPU fallback: every entry
 // point that computes something launches a CUDA kernel or fails with an error code.
 #include <algorithm>
+#include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -54,7 +55,9 @@ struct hsb_handle {
   // device staging for the host-buffer entry points
   DevBuf d_hints, d_pts, d_offsets, d_poses, d_cov, d_scratch;
   // "containers of the last match" (MapRepMultiMap::dataContainers) and the update scan
-  DevBuf d_last_pts, d_upd_pts;
+  DevBuf d_last_pts, d_upd_pts;   // single-scan buffers: 16 floats of header (hint, gate inputs), then the points
+  float* h_stage = nullptr;       // pinned staging for the single-scan calls (header + points, one H2D per call)
+  size_t h_stage_bytes = 0;
   // raw-range input (N2)
   DevBuf d_beam_cs, d_ranges, d_occ;
   hsb_scan_format fmt = hsb_scan_format();
@@ -63,6 +66,8 @@ struct hsb_handle {
   float last_origo[2] = {0.f, 0.f};
   // pinned host scratch
   float* h_pin = nullptr;  // 64 floats
+  DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
+  float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
   int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0;
   uint64_t launches = 0;
@@ -486,17 +491,55 @@ int hsb_destroy(hsb_handle* h) {
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (int l = 0; l < HSB_MAX_LEVELS; ++l) destroy_level(h, h->lv[l]);
-  DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_last_pts, &h->d_upd_pts,
+  DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_gate, &h->d_last_pts, &h->d_upd_pts,
                     &h->d_beam_cs, &h->d_ranges, &h->d_occ};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 2; ++i)
     if (h->copy_stream[i]) cudaStreamDestroy(h->copy_stream[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  return HSB_OK;
+}
+
+// Single-scan buffers carry a 16-float header in front of the points so that one copy moves both.
+static const size_t kScanHeaderFloats = 16;
+static inline float* scan_header(DevBuf& b) { return static_cast<float*>(b.p); }
+static inline float* scan_points(DevBuf& b) { return static_cast<float*>(b.p) + kScanHeaderFloats; }
+static int ensure_scan_buf(hsb_handle* h, DevBuf& b, int n) {
+  return ensure(h, b, kScanHeaderFloats * sizeof(float) + (size_t)(n > 0 ? n : 1) * 8 + 16);
+}
+// header (nh floats) + points -> pinned staging -> ONE host-to-device copy on `st`
+static int upload_scan(hsb_handle* h, DevBuf& b, const float* header, int nh, const float* pts, int n, cudaStream_t st) {
+  int s = ensure_scan_buf(h, b, n);
+  if (s != HSB_OK) return s;
+  const size_t bytes = kScanHeaderFloats * sizeof(float) + (size_t)n * 8;
+  if (bytes > h->h_stage_bytes) {
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr;
+    h->h_stage_bytes = 0;
+    size_t cap = bytes < (64u << 10) ? (64u << 10) : bytes * 2;
+    HSB_CUDA(h, cudaMallocHost(&h->h_stage, cap));
+    h->h_stage_bytes = cap;
+  }
+  memset(h->h_stage, 0, kScanHeaderFloats * sizeof(float));
+  if (nh > 0) memcpy(h->h_stage, header, (size_t)nh * sizeof(float));
+  if (n > 0) memcpy(h->h_stage + kScanHeaderFloats, pts, (size_t)n * 8);
+  HSB_CUDA(h, cudaMemcpyAsync(b.p, h->h_stage, bytes, cudaMemcpyHostToDevice, st));
+  return HSB_OK;
+}
+
+// lastMapUpdatePose = FLT_MAX^3 (HectorSlamProcessor.h:117) for the fused step
+static int reset_gate(hsb_handle* h) {
+  int s = ensure(h, h->d_gate, 4 * sizeof(float));
+  if (s != HSB_OK) return s;
+  const float init[4] = {FLT_MAX, FLT_MAX, FLT_MAX, 0.f};
+  memcpy(h->h_pin + 56, init, sizeof(init));
+  HSB_CUDA(h, cudaMemcpyAsync(h->d_gate.p, h->h_pin + 56, sizeof(init), cudaMemcpyHostToDevice, h->stream));
   return HSB_OK;
 }
 
@@ -507,6 +550,8 @@ int hsb_reset(hsb_handle* h) {
     int s = clear_level(h, l, h->stream);
     if (s != HSB_OK) return s;
   }
+  int s = reset_gate(h);
+  if (s != HSB_OK) return s;
   HSB_CUDA(h, cudaStreamSynchronize(h->stream));
   return HSB_OK;
 }
@@ -594,19 +639,15 @@ int hsb_match_data(hsb_handle* h, const float hint[3], const float* pts, int n, 
   DeviceGuard guard(h->device);
   // MapRepMultiMap::matchData fills dataContainers[] from this scan (MapRepMultiMap.h:127) whenever
   // there is a coarse level; hsb_update_by_scan reuses it for the coarse levels (:143).
-  int s = ensure(h, h->d_last_pts, (size_t)(n > 0 ? n : 1) * 8 + 16);
+  int s = ensure(h, h->d_scratch, 64 * sizeof(float));
   if (s != HSB_OK) return s;
-  s = ensure(h, h->d_scratch, 64 * sizeof(float));
-  if (s != HSB_OK) return s;
-  float* d_s = static_cast<float*>(h->d_scratch.p);  // [0..2] hint, [4..6] pose, [8..16] cov
+  float* d_s = static_cast<float*>(h->d_scratch.p);  // [4..6] pose, [8..16] cov
   cudaStream_t st = h->stream;
-  if (n > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_last_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if ((s = upload_scan(h, h->d_last_pts, hint, 3, pts, n, st)) != HSB_OK) return s;   // header [0..2] = hint
   h->last_n = n;
   h->last_origo[0] = origo ? origo[0] : 0.f;
   h->last_origo[1] = origo ? origo[1] : 0.f;
-  memcpy(h->h_pin, hint, 3 * sizeof(float));
-  HSB_CUDA(h, cudaMemcpyAsync(d_s, h->h_pin, 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-  s = hsb_match_batch_device(h, 1, d_s, static_cast<const float*>(h->d_last_pts.p), nullptr, n, n, d_s + 4, d_s + 8, st);
+  s = hsb_match_batch_device(h, 1, scan_header(h->d_last_pts), scan_points(h->d_last_pts), nullptr, n, n, d_s + 4, d_s + 8, st);
   if (s != HSB_OK) return s;
   HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 4, d_s + 4, 13 * sizeof(float), cudaMemcpyDeviceToHost, st));
   HSB_CUDA(h, cudaStreamSynchronize(st));
@@ -826,12 +867,15 @@ int hsb_match_batch_ranges(hsb_handle* h, int B, const float* hints, const float
 static int run_update(hsb_handle* h, HsbUpdateParams& P, int max_n) {
   if (max_n <= 0) return HSB_OK;
   cudaStream_t st = h->stream;
-  int blocks = (max_n + 7) / 8;
+  // mark: two warps per beam, four beams per CTA; apply: a fixed one-wave grid sweeping each level's box
+  constexpr int TEAM = 2;
+  int blocks = (max_n * TEAM + 7) / 8;
   int cap = h->sm_count * 8;
   if (blocks > cap) blocks = cap;
-  dim3 grid(blocks, P.levels);
-  hsb::update_kernel<false><<<grid, 256, 0, st>>>(P);
-  hsb::update_kernel<true><<<grid, 256, 0, st>>>(P);
+  hsb::update_mark_kernel<TEAM><<<dim3(blocks, P.levels), 256, 0, st>>>(P);
+  int sweep = (h->sm_count * 8) / (P.levels > 0 ? P.levels : 1);
+  if (sweep < 1) sweep = 1;
+  hsb::update_apply_kernel<<<dim3(sweep, P.levels), 256, 0, st>>>(P);
   h->launches += 2;
   HSB_CUDA(h, cudaGetLastError());
   return HSB_OK;
@@ -861,31 +905,30 @@ static void fill_update_level(hsb_handle* h, int l, HsbUpdateLevelDev& d) {
   d.dirty = L.dirty;
 }
 
-int hsb_update_by_scan(hsb_handle* h, const float* pts, int n, const float origo[2], const float pose[3]) {
-  if (!h || !pose || n < 0 || (n > 0 && !pts)) return HSB_ERR_INVALID_ARG;
-  DeviceGuard guard(h->device);
-  int s;
-  if ((s = ensure(h, h->d_upd_pts, (size_t)(n > 0 ? n : 1) * 8 + 16)) != HSB_OK) return s;
-  cudaStream_t st = h->stream;
-  if (n > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_upd_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+// MapRepMultiMap::updateByScan (MapRepMultiMap.h:134-147) as launches on h->stream; level 0 reads `d_pts0`,
+// the coarse levels the container the last matchData left behind (:143).  pose_dev / gate_flag: see HsbUpdateParams.
+static int enqueue_update_by_scan(hsb_handle* h, const float2* d_pts0, int n, const float origo[2], const float pose[3],
+                                  const float* pose_dev, const float* gate_flag) {
   HsbUpdateParams P;
   memset(&P, 0, sizeof(P));
   P.levels = h->levels;
-  memcpy(P.pose_world, pose, 3 * sizeof(float));
+  if (pose) memcpy(P.pose_world, pose, 3 * sizeof(float));
+  P.pose_dev = pose_dev;
+  P.gate_flag = gate_flag;
   P.log_odds_free = h->log_odds_free;
   P.log_odds_occ = h->log_odds_occ;
-  int max_n = 0;
+  int max_n = 0, s;
   for (int l = 0; l < h->levels; ++l) {
     HsbUpdateLevelDev& d = P.lv[l];
     fill_update_level(h, l, d);
     d.pt_scale = (float)(1.0 / pow(2.0, (double)l));
     if (l == 0) {  // MapRepMultiMap.h:140-141
-      d.pts = static_cast<const float2*>(h->d_upd_pts.p);
+      d.pts = d_pts0;
       d.n = n;
       d.origo_x = origo ? origo[0] : 0.f;
       d.origo_y = origo ? origo[1] : 0.f;
     } else {  // :143 — the container left behind by the last matchData
-      d.pts = static_cast<const float2*>(h->d_last_pts.p);
+      d.pts = reinterpret_cast<const float2*>(scan_points(h->d_last_pts));
       d.n = h->last_n;
       d.origo_x = h->last_origo[0];
       d.origo_y = h->last_origo[1];
@@ -897,8 +940,81 @@ int hsb_update_by_scan(hsb_handle* h, const float* pts, int n, const float origo
       if (d.n > max_n) max_n = d.n;
     }
   }
-  if ((s = run_update(h, P, max_n)) != HSB_OK) return s;
+  return run_update(h, P, max_n);
+}
+
+int hsb_update_by_scan(hsb_handle* h, const float* pts, int n, const float origo[2], const float pose[3]) {
+  if (!h || !pose || n < 0 || (n > 0 && !pts)) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int s;
+  cudaStream_t st = h->stream;
+  if ((s = upload_scan(h, h->d_upd_pts, nullptr, 0, pts, n, st)) != HSB_OK) return s;
+  if ((s = enqueue_update_by_scan(h, reinterpret_cast<const float2*>(scan_points(h->d_upd_pts)), n, origo, pose, nullptr, nullptr)) != HSB_OK)
+    return s;
   HSB_CUDA(h, cudaStreamSynchronize(st));
+  return HSB_OK;
+}
+
+int hsb_set_map_update_min_dist_diff(hsb_handle* h, float min_dist) {
+  if (!h) return HSB_ERR_INVALID_ARG;
+  h->min_dist = min_dist;
+  return HSB_OK;
+}
+int hsb_set_map_update_min_angle_diff(hsb_handle* h, float min_angle) {
+  if (!h) return HSB_ERR_INVALID_ARG;
+  h->min_angle = min_angle;
+  return HSB_OK;
+}
+
+int hsb_slam_update(hsb_handle* h, const float hint[3], const float* pts, int n, const float origo[2],
+                    int map_without_matching, float out_pose[3], float cov_inout[9], int* map_updated) {
+  if (!h || !hint || !out_pose || n < 0 || (n > 0 && !pts)) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int s;
+  if ((s = ensure(h, h->d_scratch, 64 * sizeof(float))) != HSB_OK) return s;
+  if (!h->d_gate.p && (s = reset_gate(h)) != HSB_OK) return s;
+  // scan header: [0..2] hint, [3..5] minDist / minAngle / force; scratch: [8..10] pose, [11] flag, [12..20] cov
+  float* d_s = static_cast<float*>(h->d_scratch.p);
+  float* d_gate = static_cast<float*>(h->d_gate.p);
+  cudaStream_t st = h->stream;
+  // without matching the reference leaves the coarse containers alone (HectorSlamProcessor.h:77-81,
+  // MapRepMultiMap.h:143): only level 0 sees this scan
+  DevBuf& pbuf = map_without_matching ? h->d_upd_pts : h->d_last_pts;
+  const float header[6] = {hint[0], hint[1], hint[2], h->min_dist, h->min_angle, map_without_matching ? 1.f : 0.f};
+  if ((s = upload_scan(h, pbuf, header, 6, pts, n, st)) != HSB_OK) return s;
+  const float* d_hdr = scan_header(pbuf);
+  const float* d_pose_in = d_hdr;  // the hint, unless matched below
+  if (!map_without_matching) {
+    h->last_n = n;
+    h->last_origo[0] = origo ? origo[0] : 0.f;
+    h->last_origo[1] = origo ? origo[1] : 0.f;
+    s = hsb_match_batch_device(h, 1, d_hdr, scan_points(pbuf), nullptr, n, n, d_s + 8, d_s + 12, st);  // :78
+    if (s != HSB_OK) return s;
+    d_pose_in = d_s + 8;
+  }
+  hsb::slam_gate_kernel<<<1, 32, 0, st>>>(d_gate, d_hdr + 3, d_pose_in, d_s + 8);  // :83-89
+  h->launches += 1;
+  HSB_CUDA(h, cudaGetLastError());
+  if ((s = enqueue_update_by_scan(h, reinterpret_cast<const float2*>(scan_points(pbuf)), n, origo, nullptr, d_s + 8, d_gate + 3)) != HSB_OK)  // :91
+    return s;
+  HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 8, d_s + 8, 13 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));  // :93 onMapUpdated — the probability plane is current
+  memcpy(out_pose, h->h_pin + 8, 3 * sizeof(float));
+  if (map_updated) *map_updated = h->h_pin[11] != 0.f;
+  if (cov_inout && n > 0 && !map_without_matching) memcpy(cov_inout, h->h_pin + 12, 9 * sizeof(float));
+  return HSB_OK;
+}
+
+int hsb_get_last_map_update_pose(hsb_handle* h, float out[3]) {
+  if (!h || !out) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  if (!h->d_gate.p) {
+    int s = reset_gate(h);
+    if (s != HSB_OK) return s;
+  }
+  HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 56, h->d_gate.p, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  memcpy(out, h->h_pin + 56, 3 * sizeof(float));
   return HSB_OK;
 }
 
@@ -906,9 +1022,8 @@ int hsb_update_level_by_scan(hsb_handle* h, int level, const float* pts, int n, 
   if (!h || level < 0 || level >= h->levels || !pose || n < 0 || (n > 0 && !pts)) return HSB_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
   int s;
-  if ((s = ensure(h, h->d_upd_pts, (size_t)(n > 0 ? n : 1) * 8 + 16)) != HSB_OK) return s;
   cudaStream_t st = h->stream;
-  if (n > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_upd_pts.p, pts, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if ((s = upload_scan(h, h->d_upd_pts, nullptr, 0, pts, n, st)) != HSB_OK) return s;
   HsbUpdateParams P;
   memset(&P, 0, sizeof(P));
   P.levels = 1;
@@ -918,7 +1033,7 @@ int hsb_update_level_by_scan(hsb_handle* h, int level, const float* pts, int n, 
   HsbUpdateLevelDev& d = P.lv[0];
   fill_update_level(h, level, d);
   d.pt_scale = 1.0f;
-  d.pts = static_cast<const float2*>(h->d_upd_pts.p);
+  d.pts = reinterpret_cast<const float2*>(scan_points(h->d_upd_pts));
   d.n = n;
   d.origo_x = origo ? origo[0] : 0.f;
   d.origo_y = origo ? origo[1] : 0.f;

@@ -53,7 +53,7 @@ struct HsbUpdateLevelDev {
   const float2* pts;         // scan used for this level
   int n;
   float origo_x, origo_y;    // already in the units of `pts` before pt_scale
-  uint32_t stamp_base;       // this scan's stamps: base+1 free, base+2 occupied, base+3 applied
+  uint32_t stamp_base;       // this scan's stamps: base+1 free, base+2 occupied
   int active;
   int* dirty;                // {xmin, ymin, xmax, ymax} of cells written since the last reset (device)
 };
@@ -63,6 +63,8 @@ struct HsbUpdateParams {
   int levels;
   float pose_world[3];
   float log_odds_free, log_odds_occ;
+  const float* pose_dev;     // if set, the pose is read from device memory (fused SLAM step) instead of pose_world
+  const float* gate_flag;    // if set, *gate_flag == 0 turns the launch into a no-op (slam_gate_kernel in update_kernel.cuh)
 };
 
 #endif

@@ -13,12 +13,13 @@
 //
 // The reference walks beams one after another and uses per-cell `updateIndex` stamps so that a
 // cell is touched once per scan, an end point (occupied) overriding any free marking.  That is
-// order-free, so the device does it in two grid-wide phases with one warp per beam and lanes
-// striding along the line (cell i of a Bresenham line has a closed form, no serial walk):
-//   MARK : atomicMax(stamp[cell], base+1) along the line, atomicMax(stamp[end], base+2)
-//   APPLY: the first thread to raise a marked cell's stamp to base+3 owns it and does the
-//          log-odds update (free: l += lf ; occupied: if (l < 50) l += lo) and rewrites the
-//          cell's probability (and the texture twin through a surface store).
+// order-free, so the device does it in two grid-wide phases (cell i of a Bresenham line has a
+// closed form, no serial walk):
+//   MARK : a team of warps per beam, lanes striding along the line:
+//          atomicMax(stamp[cell], base+1) along the line, atomicMax(stamp[end], base+2)
+//   APPLY: a coalesced sweep over the bounding box of the scan's beams; every cell whose stamp is
+//          base+1 / base+2 gets the log-odds update (free: l += lf ; occupied: if (l < 50) l += lo)
+//          and its probability rewritten (and the texture twin through a surface store).
 // A cell that the reference first frees and then hits ends as ((l + lf) - lf) + lo there and as
 // l + lo here — equal to ~1 ulp; tests compare planes with abs tol 1e-5.
 #ifndef HSB_UPDATE_KERNEL_CUH
@@ -124,74 +125,104 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__device__ __forceinline__ void claim_and_apply(const HsbUpdateLevelDev& L, unsigned off, float lf, float lo) {
-  const uint32_t base = L.stamp_base;
-  const uint32_t v = __ldcg(L.stamp + off);
-  if (v - (base + 1u) < 2u) {                       // marked for this scan, not yet applied
-    const uint32_t old = atomicMax(L.stamp + off, base + 3u);
-    if (old - (base + 1u) < 2u) {                   // we are the owner
-      float l = L.logodds[off];
-      if (old == base + 1u) {
-        l = __fadd_rn(l, lf);                       // updateSetFree, GridMapLogOdds.h:146-151
-      } else if (l < 50.0f) {
-        l = __fadd_rn(l, lo);                       // updateSetOccupied, GridMapLogOdds.h:135-140
-      }
-      L.logodds[off] = l;
-      const float p = prob_from_logodds(l);
-      L.prob[off] = p;
-      if (L.surf) {
-        const int y = (int)(off / (unsigned)L.sx), x = (int)(off - (unsigned)y * (unsigned)L.sx);
-        surf2Dwrite(p, L.surf, x * (int)sizeof(float), y);
-      }
-    }
+// ---- K2 -----------------------------------------------------------------------------------------
+
+// util::poseDifferenceLargerThan (util/UtilFunctions.h:73-92): float norm, the angle wrapped with double pi.
+__device__ __forceinline__ bool pose_difference_larger_than(const float* p1, const float* p2, float dist_thresh,
+                                                            float ang_thresh) {
+  const float dx = __fsub_rn(p1[0], p2[0]), dy = __fsub_rn(p1[1], p2[1]);
+  if (__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) > dist_thresh) return true;
+  float a = __fsub_rn(p1[2], p2[2]);
+  const double pi = 3.14159265358979323846, two_pi = pi * 2.0;
+  if ((double)a > pi) a = (float)((double)a - two_pi);
+  else if ((double)a < -pi) a = (float)((double)a + two_pi);
+  return fabsf(a) > ang_thresh;
+}
+
+// HectorSlamProcessor::update's gate (slam_main/HectorSlamProcessor.h:83-95) evaluated on the device so that a
+// fused step needs no host round trip between match and map write.
+//   state: [0..2] lastMapUpdatePose, [3] out: 1.0f if the map is to be written by this step
+//   in   : [0] minDist, [1] minAngle, [2] force (map_without_matching)
+// pose_out receives the step's pose (the matched pose, or the hint when matching is skipped) and, in
+// pose_out[3], a copy of the flag for the host.
+__global__ void slam_gate_kernel(float* __restrict__ state, const float* __restrict__ in, const float* pose_in,
+                                 float* pose_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float p[3] = {pose_in[0], pose_in[1], pose_in[2]};
+    const bool upd = pose_difference_larger_than(p, state, in[0], in[1]) || in[2] != 0.0f;
+    if (upd) { state[0] = p[0]; state[1] = p[1]; state[2] = p[2]; }
+    const float flag = upd ? 1.0f : 0.0f;
+    state[3] = flag;
+    pose_out[0] = p[0]; pose_out[1] = p[1]; pose_out[2] = p[2];
+    pose_out[3] = flag;
   }
 }
 
-// One warp per beam; blockIdx.y = level.  APPLY = false: mark phase, true: apply phase.
-template <bool APPLY>
-__global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ HsbUpdateParams P) {
-  const HsbUpdateLevelDev& L = P.lv[blockIdx.y];
-  if (!L.active) return;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int warp0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int warp_stride = gridDim.x * warps_per_block;
-
-  // pose in this level's cells, transform Translation(x,y)*Rotation(psi)   (OccGridMapBase.h:127-131)
-  float mx, my;
-  {
-    const float* m = L.mtw;
-    mx = __fadd_rn(__fmul_rn(m[0], P.pose_world[0]), __fadd_rn(__fmul_rn(m[1], P.pose_world[1]), m[2]));
-    my = __fadd_rn(__fmul_rn(m[3], P.pose_world[0]), __fadd_rn(__fmul_rn(m[4], P.pose_world[1]), m[5]));
-  }
-  const float c = cosf_glibc(P.pose_world[2]), s = sinf_glibc(P.pose_world[2]);  // Rotation2Df, as glibc
+// Per-level frame of one updateByScan call: the pose as Translation(x,y)*Rotation(psi) in this level's cells and
+// the common start cell of all beams (OccGridMapBase.h:127-137).
+struct BeamFrame {
+  float c, s, mx, my;
+  int x0, y0;
+  bool ok;
+};
+__device__ __forceinline__ BeamFrame beam_frame(const HsbUpdateParams& P, const HsbUpdateLevelDev& L) {
+  BeamFrame f;
+  const float* pw = P.pose_dev ? P.pose_dev : P.pose_world;
+  const float wx = pw[0], wy = pw[1], wpsi = pw[2];
+  const float* m = L.mtw;
+  f.mx = __fadd_rn(__fmul_rn(m[0], wx), __fadd_rn(__fmul_rn(m[1], wy), m[2]));
+  f.my = __fadd_rn(__fmul_rn(m[3], wx), __fadd_rn(__fmul_rn(m[4], wy), m[5]));
+  f.c = cosf_glibc(wpsi);   // Rotation2Df, as glibc
+  f.s = sinf_glibc(wpsi);
   // beam start = (int)(T * origo + 0.5)                                   (:134-137)
   const float ox = L.origo_x * L.pt_scale, oy = L.origo_y * L.pt_scale;
-  const float bxf = __fadd_rn(__fmul_rn(c, ox), __fadd_rn(__fmul_rn(-s, oy), mx));
-  const float byf = __fadd_rn(__fmul_rn(s, ox), __fadd_rn(__fmul_rn(c, oy), my));
+  const float bxf = __fadd_rn(__fmul_rn(f.c, ox), __fadd_rn(__fmul_rn(-f.s, oy), f.mx));
+  const float byf = __fadd_rn(__fmul_rn(f.s, ox), __fadd_rn(__fmul_rn(f.c, oy), f.my));
   const float bxh = __fadd_rn(bxf, 0.5f), byh = __fadd_rn(byf, 0.5f);
-  if (!(fabsf(bxh) < 1.0e9f) || !(fabsf(byh) < 1.0e9f)) return;  // non-finite / absurd pose: every beam is dropped
-  const int x0 = (int)bxh, y0 = (int)byh;
-  if ((x0 < 0) || (x0 >= L.sx) || (y0 < 0) || (y0 >= L.sy)) return;  // :176 (same start for all beams)
-  const unsigned start = (unsigned)y0 * (unsigned)L.sx + (unsigned)x0;
-  const uint32_t free_s = L.stamp_base + 1u, occ_s = L.stamp_base + 2u;
-  // dirty rectangle (for tile replication to map replicas): every written cell lies on a segment
-  // between the start cell and an end cell, so the box of those end points covers them all
-  int bx0 = x0, by0 = y0, bx1 = x0, by1 = y0;
-  bool wrote = false;
+  f.x0 = 0; f.y0 = 0;
+  f.ok = (fabsf(bxh) < 1.0e9f) && (fabsf(byh) < 1.0e9f);   // non-finite / absurd pose: every beam is dropped
+  if (f.ok) {
+    f.x0 = (int)bxh; f.y0 = (int)byh;
+    f.ok = !((f.x0 < 0) || (f.x0 >= L.sx) || (f.y0 < 0) || (f.y0 >= L.sy));   // :176 (same start for all beams)
+  }
+  return f;
+}
+// End cell of beam b; false when the reference drops the beam.
+__device__ __forceinline__ bool beam_end(const HsbUpdateLevelDev& L, const BeamFrame& f, int b, int& x1, int& y1) {
+  const float2 pt = L.pts[b];
+  const float px = pt.x * L.pt_scale, py = pt.y * L.pt_scale;   // DataPointContainer.h:46-58 setFrom
+  float exf = __fadd_rn(__fmul_rn(f.c, px), __fadd_rn(__fmul_rn(-f.s, py), f.mx));   // :148
+  float eyf = __fadd_rn(__fmul_rn(f.s, px), __fadd_rn(__fmul_rn(f.c, py), f.my));
+  exf = __fadd_rn(exf, 0.5f);                                                        // :152
+  eyf = __fadd_rn(eyf, 0.5f);
+  if (!(fabsf(exf) < 1.0e9f) || !(fabsf(eyf) < 1.0e9f)) return false;
+  x1 = (int)exf; y1 = (int)eyf;                                                      // :155
+  if (x1 == f.x0 && y1 == f.y0) return false;                                        // :158
+  if ((x1 < 0) || (x1 >= L.sx) || (y1 < 0) || (y1 >= L.sy)) return false;            // :186
+  return true;
+}
 
-  for (int b = warp0; b < L.n; b += warp_stride) {
-    const float2 pt = L.pts[b];
-    const float px = pt.x * L.pt_scale, py = pt.y * L.pt_scale;   // DataPointContainer.h:46-58 setFrom
-    float exf = __fadd_rn(__fmul_rn(c, px), __fadd_rn(__fmul_rn(-s, py), mx));   // :148
-    float eyf = __fadd_rn(__fmul_rn(s, px), __fadd_rn(__fmul_rn(c, py), my));
-    exf = __fadd_rn(exf, 0.5f);                                                  // :152
-    eyf = __fadd_rn(eyf, 0.5f);
-    if (!(fabsf(exf) < 1.0e9f) || !(fabsf(eyf) < 1.0e9f)) continue;
-    const int x1 = (int)exf, y1 = (int)eyf;                                      // :155
-    if (x1 == x0 && y1 == y0) continue;                                          // :158
-    if ((x1 < 0) || (x1 >= L.sx) || (y1 < 0) || (y1 >= L.sy)) continue;          // :186
-    const int dx = x1 - x0, dy = y1 - y0;
+// MARK: a team of TEAM warps per beam; blockIdx.y = level.  Team lanes stride along the line, four cells per
+// lane in flight (the loop is bound by the L2 round trip of the stamp test, not by arithmetic).
+template <int TEAM>
+__global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant__ HsbUpdateParams P) {
+  const HsbUpdateLevelDev& L = P.lv[blockIdx.y];
+  if (!L.active) return;
+  if (P.gate_flag && *P.gate_flag == 0.0f) return;
+  constexpr int TL = 32 * TEAM;   // lanes per team
+  constexpr int U = 4;
+  const unsigned tlane = threadIdx.x % TL;
+  const int team0 = (blockIdx.x * blockDim.x + threadIdx.x) / TL;
+  const int team_stride = (gridDim.x * blockDim.x) / TL;
+  const BeamFrame f = beam_frame(P, L);
+  if (!f.ok) return;
+  const unsigned start = (unsigned)f.y0 * (unsigned)L.sx + (unsigned)f.x0;
+  const uint32_t free_s = L.stamp_base + 1u, occ_s = L.stamp_base + 2u;
+
+  for (int b = team0; b < L.n; b += team_stride) {
+    int x1, y1;
+    if (!beam_end(L, f, b, x1, y1)) continue;
+    const int dx = x1 - f.x0, dy = y1 - f.y0;
     const unsigned adx = (unsigned)abs(dx), ady = (unsigned)abs(dy);
     const int off_dx = dx > 0 ? 1 : -1;                         // util::sign, UtilFunctions.h:56-59
     const int off_dy = (dy > 0 ? 1 : -1) * L.sx;
@@ -200,36 +231,127 @@ __global__ void __launch_bounds__(256) update_kernel(const __grid_constant__ Hsb
     if (adx >= ady) { ada = adx; adb = ady; off_a = off_dx; off_b = off_dy; }   // :202-209
     else            { ada = ady; adb = adx; off_a = off_dy; off_b = off_dx; }
     const unsigned err0 = ada / 2u;
-    // cell i (0 <= i < ada; start included, end excluded, :245-259): the serial walk adds adb per
-    // step and carries when the error reaches ada, so after i steps it has carried
-    // floor((err0 + i*adb) / ada) times.
-    for (unsigned i = (unsigned)lane; i < ada; i += 32u) {
-      const unsigned carries = (unsigned)(((unsigned long long)err0 + (unsigned long long)i * adb) / ada);
-      const unsigned off = start + (unsigned)((int)i * off_a) + (unsigned)((int)carries * off_b);
-      if (APPLY) {
-        claim_and_apply(L, off, P.log_odds_free, P.log_odds_occ);
-      } else {
-        if (__ldcg(L.stamp + off) < free_s) atomicMax(L.stamp + off, free_s);   // bresenhamCellFree :216-224
+    const bool narrow = ada < 46341u;   // err0 + i*adb < 2^31: 32-bit division
+    // cell i (0 <= i < ada; start included, end excluded, :245-259): the serial walk adds adb per step and
+    // carries when the error reaches ada, so after i steps it has carried floor((err0 + i*adb) / ada) times.
+    for (unsigned i0 = tlane; i0 < ada; i0 += U * TL) {
+      unsigned off[U];
+      uint32_t v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const unsigned i = i0 + (unsigned)(k * TL);
+        v[k] = 0xffffffffu;
+        if (i < ada) {
+          const unsigned carries = narrow ? (err0 + i * adb) / ada
+                                          : (unsigned)(((unsigned long long)err0 + (unsigned long long)i * adb) / ada);
+          off[k] = start + (unsigned)((int)i * off_a) + (unsigned)((int)carries * off_b);
+          v[k] = __ldcg(L.stamp + off[k]);
+        }
       }
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (v[k] < free_s) atomicMax(L.stamp + off[k], free_s);   // bresenhamCellFree :216-224
     }
-    if (!APPLY) {
-      bx0 = min(bx0, x1); by0 = min(by0, y1); bx1 = max(bx1, x1); by1 = max(by1, y1);
-      wrote = true;
+    if (tlane == 0) atomicMax(L.stamp + (unsigned)y1 * (unsigned)L.sx + (unsigned)x1, occ_s);   // bresenhamCellOcc :226-241, :211-212
+  }
+}
+
+// APPLY: every cell marked by this scan lies in the bounding box of the start cell and the end cells, so the
+// apply phase is a coalesced sweep of that box over the stamp plane — no atomics, one owner per cell by
+// construction.  Each CTA recomputes the box from the beams (1081 transforms, cheaper than a grid-wide
+// reduction plus a host round trip); CTA 0 also folds it into the level's dirty rectangle (tile replication).
+__device__ __forceinline__ void apply_cell(const HsbUpdateLevelDev& L, unsigned off, uint32_t v, float lf, float lo) {
+  const uint32_t d = v - (L.stamp_base + 1u);
+  if (d < 2u) {
+    float l = L.logodds[off];
+    if (d == 0u) {
+      l = __fadd_rn(l, lf);                       // updateSetFree, GridMapLogOdds.h:146-151
+    } else if (l < 50.0f) {
+      l = __fadd_rn(l, lo);                       // updateSetOccupied, GridMapLogOdds.h:135-140
     }
-    if (lane == 0) {
-      const unsigned end = (unsigned)y1 * (unsigned)L.sx + (unsigned)x1;        // :211-212
-      if (APPLY) {
-        claim_and_apply(L, end, P.log_odds_free, P.log_odds_occ);
-      } else {
-        atomicMax(L.stamp + end, occ_s);                                        // bresenhamCellOcc :226-241
-      }
+    L.logodds[off] = l;
+    const float p = prob_from_logodds(l);
+    L.prob[off] = p;
+    if (L.surf) {
+      const int y = (int)(off / (unsigned)L.sx), x = (int)(off - (unsigned)y * (unsigned)L.sx);
+      surf2Dwrite(p, L.surf, x * (int)sizeof(float), y);
     }
   }
-  if (!APPLY && wrote && lane == 0 && L.dirty) {  // one set of atomics per warp
+}
+
+__global__ void __launch_bounds__(256) update_apply_kernel(const __grid_constant__ HsbUpdateParams P) {
+  const HsbUpdateLevelDev& L = P.lv[blockIdx.y];
+  if (!L.active) return;
+  if (P.gate_flag && *P.gate_flag == 0.0f) return;
+  const BeamFrame f = beam_frame(P, L);
+  if (!f.ok) return;
+  __shared__ int red[4][8];
+  int bx0 = f.x0, by0 = f.y0, bx1 = f.x0, by1 = f.y0, any = 0;
+  for (int b = threadIdx.x; b < L.n; b += blockDim.x) {
+    int x1, y1;
+    if (beam_end(L, f, b, x1, y1)) {
+      bx0 = min(bx0, x1); by0 = min(by0, y1); bx1 = max(bx1, x1); by1 = max(by1, y1);
+      any = 1;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+    by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+    bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+    by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+  }
+  any = __syncthreads_or(any);
+  if (!any) return;
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = bx0; red[1][w] = by0; red[2][w] = bx1; red[3][w] = by1; }
+  __syncthreads();
+  for (int k = 0; k < nw; ++k) {
+    bx0 = min(bx0, red[0][k]); by0 = min(by0, red[1][k]); bx1 = max(bx1, red[2][k]); by1 = max(by1, red[3][k]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && L.dirty) {
     atomicMin(L.dirty + 0, bx0);
     atomicMin(L.dirty + 1, by0);
     atomicMax(L.dirty + 2, bx1);
     atomicMax(L.dirty + 3, by1);
+  }
+  const float lf = P.log_odds_free, lo = P.log_odds_occ;
+  const unsigned nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned rows = (unsigned)(by1 - by0 + 1);
+  constexpr int U = 4;
+  if ((L.sx & 3) == 0) {   // rows are 16-byte aligned: four cells per load
+    const unsigned xa = (unsigned)bx0 & ~3u;
+    const unsigned w4 = (((unsigned)bx1 - xa) >> 2) + 1u;
+    const unsigned total = w4 * rows;
+    for (unsigned base = tid; base < total; base += U * nthreads) {
+      unsigned off[U];
+      uint4 v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const unsigned idx = base + (unsigned)k * nthreads;
+        v[k] = make_uint4(L.stamp_base, L.stamp_base, L.stamp_base, L.stamp_base);
+        if (idx < total) {
+          const unsigned r = idx / w4, c = idx - r * w4;
+          off[k] = ((unsigned)by0 + r) * (unsigned)L.sx + xa + 4u * c;
+          v[k] = __ldcg(reinterpret_cast<const uint4*>(L.stamp + off[k]));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        apply_cell(L, off[k] + 0u, v[k].x, lf, lo);
+        apply_cell(L, off[k] + 1u, v[k].y, lf, lo);
+        apply_cell(L, off[k] + 2u, v[k].z, lf, lo);
+        apply_cell(L, off[k] + 3u, v[k].w, lf, lo);
+      }
+    }
+  } else {
+    const unsigned wd = (unsigned)(bx1 - bx0 + 1);
+    const unsigned total = wd * rows;
+    for (unsigned idx = tid; idx < total; idx += nthreads) {
+      const unsigned r = idx / wd, c = idx - r * wd;
+      const unsigned off = ((unsigned)by0 + r) * (unsigned)L.sx + (unsigned)bx0 + c;
+      apply_cell(L, off, __ldcg(L.stamp + off), lf, lo);
+    }
   }
 }
 

@@ -2,9 +2,9 @@
 //
 // Mirrors hectorslam::HectorSlamProcessor (hector_mapping/include/hector_slam_lib/slam_main/
 // HectorSlamProcessor.h:50-154) method for method — update(), reset(), the getters and setters —
-// for callers that do not have the reference's headers around.  The control flow (match, gate on
-// pose difference, write the map, bump the map epoch) stays on the host exactly as in the
-// reference; the two heavy calls go through the C-ABI to the GPU.  Where the reference's own
+// for callers that do not have the reference's headers around.  update() is one C-ABI call
+// (hsb_slam_update): match, gate on pose difference, map write and epoch bump run back to back on
+// the GPU; updateUnfused() keeps the reference's host-side control flow over the two heavy calls.  Where the reference's own
 // headers are available, use MapRepB200.h instead: it plugs into the unmodified reference façade.
 #ifndef HECTOR_SLAM_B200_SLAMPROCESSOR_HPP
 #define HECTOR_SLAM_B200_SLAMPROCESSOR_HPP
@@ -49,6 +49,20 @@ class SlamProcessor {
   // HectorSlamProcessor.h:71-113.  points: n x 2 floats in level-0 cell units (DataContainer).
   void update(const float* points_xy, int n, const float origo[2], const Pose& poseHintWorld,
               bool map_without_matching = false) {
+    // one fused call: match (:78), gate (:89), updateByScan (:91), onMapUpdated (:93) run back to back on the
+    // device; the host only mirrors the two poses the getters expose
+    const float hint[3] = {poseHintWorld.x, poseHintWorld.y, poseHintWorld.psi};
+    float out[3];
+    int updated = 0;
+    check(hsb_slam_update(h_, hint, points_xy, n, origo, map_without_matching ? 1 : 0, out, lastScanMatchCov_, &updated));
+    lastScanMatchPose_ = Pose{out[0], out[1], out[2]};  // :83
+    if (updated) lastMapUpdatePose_ = lastScanMatchPose_;  // :94
+  }
+
+  // The same step with the control flow on the host (two C-ABI calls and a round trip in between), as the
+  // reference's own HectorSlamProcessor drives MapRepB200; kept for comparison and tests.
+  void updateUnfused(const float* points_xy, int n, const float origo[2], const Pose& poseHintWorld,
+                     bool map_without_matching = false) {
     Pose newPose;
     if (!map_without_matching) {
       const float hint[3] = {poseHintWorld.x, poseHintWorld.y, poseHintWorld.psi};
@@ -80,8 +94,14 @@ class SlamProcessor {
   int getMapLevels() const { return hsb_get_map_levels(h_); }
   void setUpdateFactorFree(float f) { check(hsb_set_update_factor_free(h_, f)); }
   void setUpdateFactorOccupied(float f) { check(hsb_set_update_factor_occupied(h_, f)); }
-  void setMapUpdateMinDistDiff(float minDist) { minDist_ = minDist; }
-  void setMapUpdateMinAngleDiff(float angleChange) { minAngle_ = angleChange; }
+  void setMapUpdateMinDistDiff(float minDist) {
+    minDist_ = minDist;
+    check(hsb_set_map_update_min_dist_diff(h_, minDist));
+  }
+  void setMapUpdateMinAngleDiff(float angleChange) {
+    minAngle_ = angleChange;
+    check(hsb_set_map_update_min_angle_diff(h_, angleChange));
+  }
   // getGridMap(level): the log-odds plane, row-major [sizeY][sizeX]
   void getGridMap(int level, float* logodds_out) const { check(hsb_download_level(h_, level, logodds_out)); }
   hsb_handle* handle() { return h_; }

@@ -174,6 +174,25 @@ int hsb_update_by_scan(hsb_handle* h, const float* points_xy, int n, const float
  * level's cell units) — map/OccGridMapBase.h:121-168. */
 int hsb_update_level_by_scan(hsb_handle* h, int level, const float* points_level_xy, int n,
                              const float origo_level[2], const float robot_pose_world[3]);
+/* ---- the hot path, one SLAM step ------------------------------------------------------------*/
+/* HectorSlamProcessor::update — slam_main/HectorSlamProcessor.h:71-113 — as ONE stream-ordered
+ * sequence without a host round trip between its parts: matchData (:78; skipped and the hint taken
+ * as the pose when map_without_matching != 0, :80), the poseDifferenceLargerThan gate against the
+ * pose of the last map write (:89, util/UtilFunctions.h:73-92) evaluated on the device,
+ * updateByScan at the new pose when the gate fires (:91) and onMapUpdated (:93).  The pose of the
+ * last map write lives in the handle (FLT_MAX after hsb_create / hsb_reset, :117); the thresholds
+ * are HectorSlamProcessor::setMapUpdateMinDistDiff / setMapUpdateMinAngleDiff (:141-142, defaults
+ * 0.4 m / 0.13 rad as in :62-63).  Results equal hsb_match_data followed by a host-side gate and
+ * hsb_update_by_scan + hsb_on_map_updated.  `cov_inout` as in hsb_match_data (untouched when
+ * nothing was matched); `map_updated` (may be NULL) tells whether the map was written. */
+int hsb_set_map_update_min_dist_diff(hsb_handle* h, float min_dist);
+int hsb_set_map_update_min_angle_diff(hsb_handle* h, float min_angle);
+int hsb_slam_update(hsb_handle* h, const float pose_hint_world[3], const float* points_xy, int n,
+                    const float origo[2], int map_without_matching, float out_pose_world[3],
+                    float cov_inout[9], int* map_updated);
+/* lastMapUpdatePose of the fused step (HectorSlamProcessor.h:151) */
+int hsb_get_last_map_update_pose(hsb_handle* h, float out[3]);
+
 /* MapRepresentationInterface::onMapUpdated — MapRepMultiMap.h:107-114.  The reference bumps its
  * probability-cache epoch here; on the device the probability planes are already current, so this
  * only orders the stream (kept so the host façade reads like the reference). */
