@@ -185,6 +185,59 @@ def cpu_reference_run(world, pts, offs, hints, planes, steps: int, warmup: int, 
     return value, info
 
 
+def slam_step_latency(rep, pts, offs, hints, planes, n_gpu: int = 200, n_cpu: int = 40, with_cpu: bool = True):
+    """Secondary figure (SURVEY.md §8d config 3 use): one scan at a time through HectorSlamProcessor::update —
+    match, gate, map write — as the fused hsb_slam_update call with pageable host buffers, thresholds 0 so that
+    every step writes the map; next to it the compiled reference doing the same step on one host core (how the
+    reference runs it).  Mutates rep's map: call after everything else."""
+    import ctypes as C
+
+    nscan = min(64, hints.shape[0])
+    scans = [np.ascontiguousarray(pts[offs[i]:offs[i + 1]]) for i in range(nscan)]
+    hp = [np.ascontiguousarray(hints[i], np.float32) for i in range(nscan)]
+    rep.setMapUpdateMinDistDiff(0.0)
+    rep.setMapUpdateMinAngleDiff(0.0)
+    o_pose, o_cov, upd = np.zeros(3, np.float32), np.zeros(9, np.float32), C.c_int(0)
+    lib, hnd = rep.lib, rep.h
+    lat = []
+    for i in range(n_gpu + 20):
+        k = i % nscan
+        t0 = time.perf_counter()
+        st = lib.hsb_slam_update(hnd, hp[k].ctypes.data, scans[k].ctypes.data, scans[k].shape[0], None, 0,
+                                 o_pose.ctypes.data, o_cov.ctypes.data, C.addressof(upd))
+        t1 = time.perf_counter()
+        if st != 0:
+            raise RuntimeError("hsb_slam_update failed")
+        if i >= 20:
+            lat.append(t1 - t0)
+    lat = np.sort(np.asarray(lat)) * 1e6
+    out = {"call": "hsb_slam_update (match + gate + updateByScan + onMapUpdated, one scan, host buffers)",
+           "gpu_us_p50": float(lat[len(lat) // 2]), "gpu_us_p99": float(lat[int(0.99 * (len(lat) - 1))]),
+           "steps": n_gpu, "budget_us_at_40hz": 25000.0}
+    if with_cpu:
+        from oracle import pyoracle
+
+        kind = "reference" if pyoracle.available("reference") else "port"
+        orc = pyoracle.Oracle(kind, RES, MAP_SIZE, LEVELS)
+        orc.set_update_factors(0.4, 0.9)
+        orc.set_map_update_thresholds(0.0, 0.0)
+        for l in range(LEVELS):
+            orc.set_logodds(l, planes[l])
+        cl = []
+        for i in range(n_cpu + 5):
+            k = i % nscan
+            t0 = time.perf_counter()
+            orc.update(scans[k], hp[k])
+            t1 = time.perf_counter()
+            if i >= 5:
+                cl.append(t1 - t0)
+        orc.close()
+        out["cpu_reference_us_p50"] = float(np.median(cl) * 1e6)
+        out["cpu_kind"] = kind
+        out["cpu_cores"] = 1
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -349,13 +402,13 @@ def main():
     rep.set_scan_format(**synth.SCAN_FORMAT)
     # host buffers local to the GPU's NUMA node (restored before the CPU baseline uses all cores)
     prev_affinity = parallel.bind_process_to_gpu_numa_node(local_rank)
-    h_ranges = torch.from_numpy(np.ascontiguousarray(make_workload.ranges)).pin_memory()
-    h_pts = torch.from_numpy(pts).pin_memory()
-    h_hints = torch.from_numpy(hints).pin_memory()
+    h_ranges = parallel.pinned_copy(np.ascontiguousarray(make_workload.ranges))
+    h_pts = parallel.pinned_copy(pts)
+    h_hints = parallel.pinned_copy(hints)
     h_offs = torch.from_numpy(offs)
-    h_poses = torch.empty((B, 3), dtype=torch.float32).pin_memory()
-    h_cov = torch.empty((B, 9), dtype=torch.float32).pin_memory()
-    h_poses2 = torch.empty((B, 3), dtype=torch.float32).pin_memory()
+    h_poses = parallel.pinned_empty((B, 3))
+    h_cov = parallel.pinned_empty((B, 9))
+    h_poses2 = parallel.pinned_empty((B, 3))
 
     def step_e2e():
         rep.match_batch_ranges(h_hints, h_ranges, want_cov=True, out_poses=h_poses, out_cov=h_cov)
@@ -432,6 +485,8 @@ def main():
         if not args.no_cpu_baseline and world_size == 1:
             _, info = cpu_reference_run(world, pts, offs, hints, planes_host, steps=3, warmup=1, max_seconds=16.0)
             line["cpu_baseline"] = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if world_size == 1:
+            line["slam_step"] = slam_step_latency(rep, pts, offs, hints, planes_host, with_cpu=not args.no_cpu_baseline)
         print(json.dumps(line), flush=True)
     rep.close()
     if world_size > 1:

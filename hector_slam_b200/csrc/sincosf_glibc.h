@@ -128,5 +128,38 @@ HSB_HD float cosf_glibc(float y) {
   return (float)cos(x);
 }
 
+// sinf_glibc and cosf_glibc of the same argument with ONE argument reduction: the two polynomials are the ones the
+// separate functions evaluate (n even: sin from the sine polynomial, cos from the cosine polynomial; n odd: swapped),
+// so both results are bit-identical to the separate calls (tests/test_sincosf_glibc.py).
+HSB_HD void sincosf_glibc(float y, float* sp, float* cp) {
+  const double x = (double)y;
+  const uint32_t top = (f32_bits(y) >> 20) & 0x7ffu;
+  if (top <= 0x3f3u) {                 // |y| < pi/4
+    if (top <= 0x397u) {               // |y| < 2^-12
+      *sp = y;
+      *cp = 1.0f;
+      return;
+    }
+    const double x2 = HSB_DMUL(x, x);
+    *sp = (float)sc_sin_poly(x, x2);
+    *cp = (float)sc_cos_poly(x2, false);
+    return;
+  }
+  if (top <= 0x42eu) {                 // |y| < 120
+    int n;
+    const double xr = sc_reduce(x, &n);
+    const double x2 = HSB_DMUL(xr, xr);
+    const double sign = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    const float a = (float)sc_sin_poly(HSB_DMUL(xr, sign), x2);
+    const float b = (float)sc_cos_poly(x2, (n & 2) != 0);
+    const bool even = (n & 1) == 0;
+    *sp = even ? a : b;
+    *cp = even ? b : a;
+    return;
+  }
+  *sp = (float)sin(x);
+  *cp = (float)cos(x);
+}
+
 }  // namespace hsb
 #endif

@@ -143,10 +143,10 @@ __device__ __forceinline__ bool pose_difference_larger_than(const float* p1, con
 // fused step needs no host round trip between match and map write.
 //   state: [0..2] lastMapUpdatePose, [3] out: 1.0f if the map is to be written by this step
 //   in   : [0] minDist, [1] minAngle, [2] force (map_without_matching)
-// pose_out receives the step's pose (the matched pose, or the hint when matching is skipped) and, in
-// pose_out[3], a copy of the flag for the host.
+// pose_out (device) and pose_out_host (mapped host memory, may be null) receive the step's pose (the matched
+// pose, or the hint when matching is skipped) and, in [3], a copy of the flag.
 __global__ void slam_gate_kernel(float* __restrict__ state, const float* __restrict__ in, const float* pose_in,
-                                 float* pose_out) {
+                                 float* pose_out, float* pose_out_host) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const float p[3] = {pose_in[0], pose_in[1], pose_in[2]};
     const bool upd = pose_difference_larger_than(p, state, in[0], in[1]) || in[2] != 0.0f;
@@ -155,6 +155,10 @@ __global__ void slam_gate_kernel(float* __restrict__ state, const float* __restr
     state[3] = flag;
     pose_out[0] = p[0]; pose_out[1] = p[1]; pose_out[2] = p[2];
     pose_out[3] = flag;
+    if (pose_out_host) {   // mapped pinned host memory: the result needs no copy operation
+      pose_out_host[0] = p[0]; pose_out_host[1] = p[1]; pose_out_host[2] = p[2];
+      pose_out_host[3] = flag;
+    }
   }
 }
 

@@ -14,12 +14,12 @@ rep.set_scan_format(**synth.SCAN_FORMAT)
 from hector_slam_b200 import parallel
 if len(sys.argv) > 1 and sys.argv[1] == "bind":
     print("affinity before:", len(os.sched_getaffinity(0)), "bound ->", parallel.bind_process_to_gpu_numa_node(0) is not None, len(os.sched_getaffinity(0)))
-h_ranges = torch.from_numpy(np.ascontiguousarray(bench.make_workload.ranges)).pin_memory()
-h_pts = torch.from_numpy(pts).pin_memory()
-h_hints = torch.from_numpy(hints).pin_memory()
-h_offs_pin = torch.from_numpy(offs).pin_memory()
-h_poses = torch.empty((B, 3), dtype=torch.float32).pin_memory()
-h_cov = torch.empty((B, 9), dtype=torch.float32).pin_memory()
+h_ranges = parallel.pinned_copy(np.ascontiguousarray(bench.make_workload.ranges))
+h_pts = parallel.pinned_copy(pts)
+h_hints = parallel.pinned_copy(hints)
+h_offs_pin = parallel.pinned_copy(offs)
+h_poses = parallel.pinned_empty((B, 3))
+h_cov = parallel.pinned_empty((B, 9))
 
 def timeit(fn, n=20):
     for _ in range(5): fn()
@@ -32,7 +32,7 @@ d = torch.empty_like(h_pts, device="cuda")
 ms = timeit(lambda: d.copy_(h_pts, non_blocking=True)); print(f"H2D {h_pts.numel()*4/1e6:.1f} MB: {ms:.3f} ms  {h_pts.numel()*4/ms/1e6:.1f} GB/s")
 d2 = torch.empty_like(h_ranges, device="cuda")
 ms = timeit(lambda: d2.copy_(h_ranges, non_blocking=True)); print(f"H2D {h_ranges.numel()*4/1e6:.1f} MB: {ms:.3f} ms  {h_ranges.numel()*4/ms/1e6:.1f} GB/s")
-for chunk in (4096, 2048, 1366, 1024, 683, 512):
+for chunk in (0, 4096, 1024):
     rep.set_tuning(chunk=chunk)
     a = timeit(lambda: rep.match_batch_ranges(h_hints, h_ranges, want_cov=True, out_poses=h_poses, out_cov=h_cov))
     b = timeit(lambda: rep.match_batch(h_hints, h_pts, h_offs_pin, want_cov=True, out_poses=h_poses, out_cov=h_cov))

@@ -23,10 +23,16 @@ int main() {
     ++n;
     if (hsb::sinf_glibc(x) != sinf(x)) ++bad;
     if (hsb::cosf_glibc(x) != cosf(x)) ++bad;
+    float sc, cc; hsb::sincosf_glibc(x, &sc, &cc);
+    if (sc != sinf(x) || cc != cosf(x)) ++bad;
   }
   const float edge[] = {0.f, -0.f, 0.78539816f, 0.785398185f, 0.78539822f, 1.5707963f, 3.1415927f, -3.1415927f, 6.2831855f,
                         2.4414062e-4f, 2.4414065e-4f, 119.99999f};
-  for (float x : edge) { if (hsb::sinf_glibc(x) != sinf(x)) ++bad; if (hsb::cosf_glibc(x) != cosf(x)) ++bad; }
+  for (float x : edge) {
+    if (hsb::sinf_glibc(x) != sinf(x)) ++bad; if (hsb::cosf_glibc(x) != cosf(x)) ++bad;
+    float sc, cc; hsb::sincosf_glibc(x, &sc, &cc);
+    if (sc != sinf(x) || cc != cosf(x)) ++bad;
+  }
   std::printf("%ld %ld\n", n, bad);
   return bad ? 1 : 0;
 }
