@@ -139,3 +139,19 @@ def test_two_ranks_gloo(pyoracle):
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] for r in results), results
     assert sorted(r[2] for r in results) == [(0, 8), (8, 16)]
+
+
+def test_cpulist_parsing_and_numa_binding_without_gpu():
+    """Host plumbing of the e2e path: sysfs cpulist parsing; binding degrades to a no-op (None) where there is no
+    CUDA device or no sysfs entry, and never raises."""
+    from hector_slam_b200 import parallel
+
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parallel._parse_cpulist("") == set()
+    assert parallel._parse_cpulist("5") == {5}
+    import torch
+
+    if not torch.cuda.is_available():
+        before = os.sched_getaffinity(0)
+        assert parallel.bind_process_to_gpu_numa_node(0) is None
+        assert os.sched_getaffinity(0) == before
