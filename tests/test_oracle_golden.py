@@ -171,3 +171,41 @@ def test_port_equals_reference_on_fresh_inputs(pyoracle, oracle_kinds):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     for l in range(3):
         assert np.array_equal(res[0][2][l], res[1][2][l])
+
+
+def test_reference_sensitivity_on_a_sparse_map(pyoracle, oracle_kinds):
+    """How much the REFERENCE's own answer moves under mathematically irrelevant changes on the first steps of a
+    SLAM stream (map written once or twice, i.e. sparse): (a) the scan's points summed in reverse / rotated order,
+    (b) the hint moved by 3e-5 (m, m, rad).  Measured with the compiled reference: on this 2048^2 stream most steps
+    are bit-stable, but several move by 1e-4 .. 4e-4 — bilinear interpolation makes the objective piecewise, a
+    last-bit difference can tip an endpoint into the neighbouring cell, and 14 evaluations do not always reach the
+    fixed point on a one-scan map.  So the 1e-4 parity bar of the GPU tests is, on sparse maps, tighter than the
+    reference's own reproducibility; that the GPU stream tests pass it is a property of the shipped reduction order
+    ("A finding about parity on sparse maps").  This test pins the fact, with the oracle only."""
+    from hector_slam_b200 import synth
+
+    size = 2048
+    world = synth.World.for_map_size(size)
+    orc = pyoracle.Oracle(oracle_kinds[0], 0.05, size, 3)
+    orc.set_update_factors(0.4, 0.9)
+    orc.set_map_update_thresholds(0.4, 0.9)
+    pose = np.array([3.0, 2.0, 0.1])
+    rng = np.random.default_rng(5)
+    hint = pose.astype(np.float32)
+    order, hintsens = [], []
+    for k in range(36):
+        scan = np.ascontiguousarray(synth.make_scan(world, pose, rng))
+        fwd, _ = orc.match(hint, scan)
+        rev, _ = orc.match(hint, np.ascontiguousarray(scan[::-1]))
+        rot, _ = orc.match(hint, np.ascontiguousarray(np.roll(scan, 137, axis=0)))
+        per, _ = orc.match((hint + np.array([3e-5, -3e-5, 3e-5], np.float32)).astype(np.float32), scan)
+        order.append(float(max(np.abs(fwd - rev).max(), np.abs(fwd - rot).max())))
+        hintsens.append(float(np.abs(per - fwd).max()))
+        hint, _ = orc.update(scan, hint)
+        h = pose[2]
+        pose = pose + np.array([0.0125 * np.cos(h), 0.0125 * np.sin(h), 0.0075])
+    orc.close()
+    order, hintsens = np.asarray(order), np.asarray(hintsens)
+    assert np.median(order) <= 1e-6                         # most steps: order does not matter at all
+    assert max(order.max(), hintsens.max()) >= 1e-4         # some steps: the reference itself moves past the bar
+    assert max(order.max(), hintsens.max()) <= 2e-3         # ... but not arbitrarily far
