@@ -28,6 +28,9 @@ NVCC_FLAGS = [
     # like the reference's; ptxas would otherwise fuse even mul.rn.f32x2 + add.rn.f32x2 into FFMA2.
     # Fused operations are written explicitly (fmaf / __ffma2_rn) where they are wanted.
     "-fmad=false",
+    # host code too: the bit-exact host arithmetic (affine maps, beam table) must not be contracted on
+    # targets whose baseline ISA has FMA (aarch64); GCC defaults to -ffp-contract=fast
+    "-Xcompiler", "-ffp-contract=off",
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "static",
 ]
@@ -70,7 +73,7 @@ def build_host(force: bool = False) -> str | None:
     if not force and _newer(HOST_LIB, srcs):
         return HOST_LIB
     cxx = shutil.which("g++") or "g++"
-    cmd = [cxx, "-std=c++14", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", HOST, src,
+    cmd = [cxx, "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", HOST, src,
            "-o", HOST_LIB, "-L", LIBDIR, "-lhsb200", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

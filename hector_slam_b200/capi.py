@@ -30,6 +30,7 @@ EXPORTED = [
     "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
     "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch",
     "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device", "hsb_raycast_batch",
+    "hsb_read_trace", "hsb_get_last_launch_shape",
 ]
 
 
@@ -122,6 +123,8 @@ def load_library() -> C.CDLL:
     sig("hsb_likelihood_batch", i, vp, i, i, vp, vp, vp, i, vp)
     sig("hsb_get_dirty_rect", i, vp, i, vp, i)
     sig("hsb_raycast_batch", i, vp, i, i, vp, vp, vp, vp)
+    sig("hsb_read_trace", i, vp, vp, i)
+    sig("hsb_get_last_launch_shape", i, vp, vp)
     sig("hsb_pack_rect_device", i, vp, i, vp, vp, vp)
     sig("hsb_unpack_rect_device", i, vp, i, vp, vp, vp)
     _lib = L
@@ -193,6 +196,19 @@ class MapRepB200:
     def set_tuning(self, **kw):
         for k, v in kw.items():
             self._check(self.lib.hsb_set_tuning(self.h, k.encode(), int(v)))
+
+    def last_launch_shape(self) -> dict:
+        out = (C.c_int * 6)()
+        self._check(self.lib.hsb_get_last_launch_shape(self.h, out))
+        return dict(zip(("warps_per_scan", "scans_per_block", "unroll", "staged_points", "grid", "resident_ctas"),
+                        (int(v) for v in out)))
+
+    def read_trace(self, max_scans: int) -> np.ndarray:
+        out = np.zeros((max_scans, 8), np.uint64)
+        n = self.lib.hsb_read_trace(self.h, out.ctypes.data, max_scans)
+        if n < 0:
+            self._check(n)
+        return out[:n]
 
     @property
     def launch_count(self) -> int:

@@ -72,7 +72,10 @@ struct hsb_handle {
   DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
   float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0;
+  DevBuf d_trace;
+  int trace_scans = 0;
+  int last_shape[6] = {0, 0, 0, 0, 0, 0};  // W, G, U, staged points per scan (0 = none), grid, resident CTAs / SM
   uint64_t launches = 0;
   std::string err;
 };
@@ -224,14 +227,26 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
   };
   if (cap > 0 && !P.ranges && h->tune_stage_smem == 1) {
     // Wave quantisation (profiles/r01_sweep_large_batches.log): staging costs ~9 KB of shared memory
-    // per scan, i.e. fewer resident groups.  If the batch does not fit the resident groups WITH
-    // staging but does fit WITHOUT (one wave instead of one and a bit), read the endpoints through
-    // L1 instead — measured 28.5 vs 24.5 M matches/s at B = 4096.
+    // per scan, i.e. fewer resident groups.  If the batch does not fit the resident groups WITH the
+    // whole scan staged but does fit WITHOUT (one wave instead of one and a bit), stage only the prefix
+    // of each scan that the shared memory of a one-wave residency affords and read the rest through
+    // L1 (tuning "partial" = 0: stage nothing in that case, the round-1 behaviour).
     const long groups = ((long)P.B + G - 1) / G;
     const long slots_staged = (long)resident(header + (size_t)G * cap * 8) * h->sm_count;
     const long slots_plain = (long)resident(header) * h->sm_count;
-    if (groups > slots_staged && groups <= slots_plain) cap = 0;
+    if (groups > slots_staged && groups <= slots_plain) {
+      cap = 0;
+      if (h->tune_partial && !PACK) {
+        const long need = (groups + h->sm_count - 1) / h->sm_count;       // CTAs per SM for one wave
+        const long budget = 232448 / need - 1024 - (long)header;          // bytes of points per CTA
+        const int gt = W * 32;
+        int pts = (int)(budget / 8 / G);
+        pts = (pts - 2) / gt * gt;
+        if (pts >= 4 * gt) cap = pts + 2;
+      }
+    }
   }
+  P.prefetch = h->tune_prefetch;
   P.pts_cap = cap;
   size_t smem = header + (size_t)G * cap * 8;
   if (smem > 48 * 1024) {
@@ -247,10 +262,21 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
     // (function attributes are per device: set on every launch rather than cached per process)
     HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
   }
+  P.trace = nullptr;
+  if (h->tune_trace) {
+    int s = ensure(h, h->d_trace, (size_t)P.B * 64);
+    if (s != HSB_OK) return s;
+    P.trace = static_cast<unsigned long long*>(h->d_trace.p);
+    h->trace_scans = P.B;
+  }
   const int seq = h->tune_seq > 0 ? h->tune_seq : 1;  // scans each group handles one after the other
   int grid = (P.B + G * seq - 1) / (G * seq);
   kern<<<grid, W * G * 32, smem, st>>>(P);
   h->launches++;
+  {
+    const int shape[6] = {W, G, U, cap > 0 ? (cap > max_n ? max_n : ((cap - 2) / (W * 32)) * (W * 32)) : 0, grid, resident(smem)};
+    memcpy(h->last_shape, shape, sizeof(shape));
+  }
   HSB_CUDA(h, cudaGetLastError());
   return HSB_OK;
 }
@@ -374,6 +400,20 @@ static std::string g_create_error;
 const char* hsb_last_error(const hsb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 uint64_t hsb_get_launch_count(const hsb_handle* h) { return h ? h->launches : 0; }
+
+int hsb_get_last_launch_shape(const hsb_handle* h, int out[6]) {
+  if (!h || !out) return HSB_ERR_INVALID_ARG;
+  memcpy(out, h->last_shape, sizeof(h->last_shape));
+  return HSB_OK;
+}
+
+int hsb_read_trace(hsb_handle* h, uint64_t* out, int max_scans) {
+  if (!h || !out || max_scans < 0) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  const int n = std::min(max_scans, h->trace_scans);
+  if (n > 0) HSB_CUDA(h, cudaMemcpy(out, h->d_trace.p, (size_t)n * 64, cudaMemcpyDeviceToHost));
+  return n;
+}
 int hsb_get_gather_mode(const hsb_handle* h) { return h ? h->gather_mode : 0; }
 
 int hsb_create(const hsb_config* cfg, hsb_handle** out) {
@@ -507,7 +547,7 @@ int hsb_destroy(hsb_handle* h) {
   cudaDeviceSynchronize();
   for (int l = 0; l < HSB_MAX_LEVELS; ++l) destroy_level(h, h->lv[l]);
   DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_gate, &h->d_last_pts, &h->d_upd_pts,
-                    &h->d_beam_cs, &h->d_ranges, &h->d_occ};
+                    &h->d_beam_cs, &h->d_ranges, &h->d_occ, &h->d_trace};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -598,6 +638,9 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "packed")) h->tune_packed = value;
   else if (!strcmp(key, "seq")) h->tune_seq = value;
   else if (!strcmp(key, "host_out")) h->tune_host_out = value;
+  else if (!strcmp(key, "partial")) h->tune_partial = value;
+  else if (!strcmp(key, "prefetch")) h->tune_prefetch = value;
+  else if (!strcmp(key, "trace")) h->tune_trace = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }

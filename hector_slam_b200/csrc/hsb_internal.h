@@ -40,6 +40,9 @@ struct HsbMatchParams {
   float range_min, range_max_c;  // keep range_min < r < range_max - 0.1
   float scale_to_map;
   float neg_zero;           // -0.0f, deliberately opaque to the compiler (see mul2_exact in match_kernel.cuh)
+  int prefetch;             // != 0: L2 bulk prefetch of the part of a scan that is read from global memory
+  // diagnostics (hsb_set_tuning "trace"): per scan 8 x u64 = {start, after coarsest level, ..., end (slot 1+levels), -, smid (slot 7)}
+  unsigned long long* trace;
 };
 
 struct HsbUpdateLevelDev {

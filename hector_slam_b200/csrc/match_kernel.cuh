@@ -423,6 +423,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// L2 prefetch of [from, to) (rounded inwards to 16-byte units): one instruction for a whole scan.
+__device__ __forceinline__ void l2_prefetch(const void* from, const void* to) {
+  const uintptr_t a = ((uintptr_t)from + 15) & ~(uintptr_t)15, b = (uintptr_t)to & ~(uintptr_t)15;
+  if (b > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((uint32_t)(b - a)) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+__device__ __forceinline__ unsigned sm_id() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
 // Barrier among the W warps of group g.  The id must be an immediate: with a register operand
 // ptxas reserves all 16 named barriers for the CTA, and the SM's barrier budget then caps
 // residency at 4 CTAs (measured with ncu: launch__occupancy_limit_barriers).
@@ -539,20 +554,27 @@ __global__ void __launch_bounds__(W * G * 32)
       n = P.n_shared;
     }
     const float2* __restrict__ gpts = P.pts + beg;
-    const float2* spts_scan = spts;  // shared-memory copy of the scan (valid when staged)
+    const float2* spts_scan = spts;  // shared-memory copy of the scan's first `ns` points (valid when staged)
     bool staged = false;
+    int ns = 0;                      // points [0, ns) are read from shared memory, [ns, n) from global memory
+    if (P.trace && t == 0) P.trace[8 * (size_t)scan] = global_timer_ns();
     if (P.ranges) {
       // raw ranges in: convert + compact straight into shared memory (host guarantees cap >= n_beams)
       n = stage_from_ranges<W>(P.ranges + (size_t)scan * P.n_beams, P.beam_cs, P.n_beams, P.range_min, P.range_max_c,
                                P.scale_to_map, spts, warp_cnt, g, w, lane);
+      ns = n;
       staged = true;
-    } else if (cap > 0 && n < cap && n > 0) {
-      // Stage the scan into shared memory.  Point i goes to spts[i + head] where head = 1 iff the
+    } else if (cap > 0 && n > 0 && (n < cap || (!PACK && cap - 2 >= GT))) {
+      // Stage the scan — or, when it does not fit the `cap` slots the launcher could afford per group
+      // (wave quantisation, hsb_api.cu launch_match_t), a prefix of it whose length is a multiple of the
+      // group size, so that every lane keeps its endpoints and visits them in the same order: results
+      // do not depend on how much was staged.  Point i goes to spts[i + head] where head = 1 iff the
       // scan starts on an odd point (8- but not 16-byte aligned), so that global and shared
       // addresses share their 16-byte phase and the even-aligned body can move as ONE bulk copy;
       // a misaligned first point / odd last point is carried by plain stores.
+      ns = n < cap ? n : ((cap - 2) / GT) * GT;
       const int head = (int)(((uintptr_t)gpts >> 3) & 1);
-      const int body = (n - head) & ~1;
+      const int body = (ns - head) & ~1;
       float2* sdst = spts + head;
       if (t == 0) {
         if (body > 0) {
@@ -561,8 +583,9 @@ __global__ void __launch_bounds__(W * G * 32)
           bulk_g2s(sdst + head, gpts + head, (uint32_t)body * 8u, mbar);
         }
         if (head) sdst[0] = gpts[0];
-        if (head + body < n) sdst[n - 1] = gpts[n - 1];
+        if (head + body < ns) sdst[ns - 1] = gpts[ns - 1];
       }
+      if (P.prefetch && t == 0 && ns < n) l2_prefetch(gpts + ns, gpts + n);
       if (body > 0) {
         mbar_wait(mbar, phase);
         phase ^= 1u;
@@ -570,10 +593,12 @@ __global__ void __launch_bounds__(W * G * 32)
       group_sync<W>(g);  // head/tail stores visible to the whole group
       spts_scan = sdst;
       staged = true;
+    } else if (P.prefetch && t == 0 && n > 0) {
+      l2_prefetch(gpts, gpts + n);
     }
 
     int pack_head = 0;
-    if (PACK && staged) {
+    if (PACK && staged) {   // (the packed path is only taken with the whole scan staged: ns == n)
       pack_head = (int)(spts_scan - spts);
       pairify_in_place<W>(spts, pack_head, n, t);
       group_sync<W>(g);
@@ -604,9 +629,10 @@ __global__ void __launch_bounds__(W * G * 32)
           acc_zero(a);
           if (PACK && staged)
             eval_pairs<(U + 1) / 2>(LR, reinterpret_cast<const float4*>(spts), t, GT, npairs, cs, ss, ex, ey, P.neg_zero, a);
-          else if (staged)
-            eval_points<MODE, U>(LR, spts_scan, t, GT, n, cs, ss, ex, ey, a);
-          else
+          else if (staged) {
+            eval_points<MODE, U>(LR, spts_scan, t, GT, ns, cs, ss, ex, ey, a);
+            if (ns < n) eval_points<MODE, U>(LR, gpts, ns + t, GT, n, cs, ss, ex, ey, a);
+          } else
             eval_points<MODE, U>(LR, gpts, t, GT, n, cs, ss, ex, ey, a);
           warp_reduce(a);
           if (W > 1) {
@@ -654,7 +680,12 @@ __global__ void __launch_bounds__(W * G * 32)
         epsi = normalize_angle(epsi);                 // ScanMatcher.h:170
         affine_apply_exact(L.wtm, ex, ey, wx, wy);    // :186 getWorldCoordsPose
         wpsi = epsi;
+        if (P.trace && t == 0) P.trace[8 * (size_t)scan + (P.levels - lvl)] = global_timer_ns();
       }
+    }
+    if (P.trace && t == 0) {
+      P.trace[8 * (size_t)scan + 1 + P.levels] = global_timer_ns();
+      P.trace[8 * (size_t)scan + 7] = sm_id();
     }
     if (t == 0) {
       P.out_poses[3 * scan + 0] = wx;

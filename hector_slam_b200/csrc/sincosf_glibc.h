@@ -14,6 +14,16 @@
 // from that library's __sincosf_table.  tests/test_sincosf_glibc.py checks the host build of
 // this header against the running libm bit for bit over tens of millions of arguments.
 //
+// Provenance / licence: this header is a restatement of the GNU C Library's single-precision
+// sin/cos algorithm (glibc 2.39, sysdeps/ieee754/flt-32/{s_sinf.c,s_cosf.c,sincosf.h,
+// sincosf_data.c}; Copyright (C) Free Software Foundation, Inc., contributed by Arm Ltd.,
+// licensed LGPL-2.1-or-later).  The polynomial coefficients and the operation order are glibc's
+// (they have to be, that is the point); no glibc source text is included.  Treat this file as
+// LGPL-2.1-or-later derived material when redistributing.
+// Platform note: "as glibc evaluates them" means the x86-64 FMA ifunc variant; on an aarch64 host
+// (Grace) glibc's generic build uses the same algorithm with compiler-chosen contraction, so a
+// reference running there may differ in the last bit and the table below would need re-pinning.
+//
 // Arguments with |y| >= 120 (glibc's table-driven large-argument reduction) fall back to a
 // correctly rounded evaluation; pose angles are normalised to (-pi, pi] once per level.
 #ifndef HSB_SINCOSF_GLIBC_H

@@ -255,8 +255,17 @@ uint64_t hsb_get_launch_count(const hsb_handle* h);
 int hsb_get_gather_mode(const hsb_handle* h);
 /* launch-shape knobs for experiments: "warps_per_scan" (0 = auto), "scans_per_block" (0 = auto),
  * "stage_smem" (1 = stage scan endpoints in shared memory), "chunk" (scans per pipeline chunk of
- * hsb_match_batch, 0 = auto).  Results never depend on them beyond summation order. */
+ * hsb_match_batch, 0 = auto), "partial" (1 = stage a prefix of each scan when the whole scan would cost a wave),
+ * "prefetch" (1 = L2 bulk prefetch of the unstaged part of a scan), "unroll", "trace" (see hsb_read_trace).  Results never depend on them beyond summation order. */
 int hsb_set_tuning(hsb_handle* h, const char* key, int value);
+/* Shape of the last match-kernel launch of this handle: {warps per scan, scans per CTA, gather batch (unroll),
+ * endpoints of each scan staged in shared memory (0 = read through L1), grid size, resident CTAs per SM}.
+ * Lets tests assert WHICH instantiation they compared with the oracle. */
+int hsb_get_last_launch_shape(const hsb_handle* h, int out[6]);
+/* Timeline of the last match launch when the tuning key "trace" is set: per scan 8 x uint64 =
+ * {%globaltimer at start, after each level (coarsest first), at the end (slot 1 + levels), ..., %smid (slot 7)}.
+ * Synchronises the device; returns the number of scans copied (<= max_scans) or a negative status. */
+int hsb_read_trace(hsb_handle* h, uint64_t* out, int max_scans);
 /* library build identification, e.g. "hector_slam_b200 0.1 sm_100a" */
 const char* hsb_version(void);
 

@@ -5,7 +5,7 @@
  * /root/reference/hector_mapping/include/hector_slam_lib/).  No Eigen: every small fixed-size
  * operation is written out in the evaluation order oracle/shim fixes for it (see shim/Eigen/Core
  * and shim/Eigen/Geometry), so that this file and oracle/_ref/libhsref.so (the unmodified
- * reference headers on the shim) agree BIT FOR BIT — tests/test_oracle_port_vs_reference.py
+ * reference headers on the shim) agree BIT FOR BIT — tests/test_oracle_golden.py
  * asserts exactly that wherever /root/reference or the prebuilt _ref library is available.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / `--impl reference` legs may

@@ -57,10 +57,3 @@ def test_create_without_gpu_fails_loudly(hsb_lib):
         assert e.status == -4
     else:
         raise AssertionError("hsb_create succeeded without a GPU")
-
-
-def test_host_constants_match_oracle(hsb_lib, pyoracle):
-    """The per-level affine maps are computed on the host by the library (hsb_create) with the
-    reference's fp32 sequence — but hsb_create needs a device, so this check lives in the GPU
-    suite (tests/test_gpu_match.py::test_pose_conversions)."""
-    assert True

@@ -14,18 +14,23 @@ import time
 import numpy as np
 import pytest
 
-from conftest import pose_err
+from conftest import pose_err, report
 
 pytestmark = pytest.mark.gpu
 
 
-def build_pair(pyoracle, size, levels=3):
+def best_kind(oracle_kinds):
+    """The compiled reference (oracle/_ref) wherever it travelled to, else the C port (pinned bit-exact to it)."""
+    return "reference" if "reference" in oracle_kinds else "port"
+
+
+def build_pair(pyoracle, size, levels=3, kind="port"):
     """CPU oracle with a map of the synthetic world (known-pose mapping) + a GPU handle holding a
     bit-identical copy of its planes."""
     from hector_slam_b200 import capi, synth
 
     world = synth.World.for_map_size(size)
-    orc = pyoracle.Oracle("port", 0.05, size, levels)
+    orc = pyoracle.Oracle(kind, 0.05, size, levels)
     orc.set_update_factors(0.4, 0.9)
     pyoracle.build_map_known_poses(orc, world)
     rep = capi.MapRepB200(0.05, size, levels=levels, update_factor_free=0.4, update_factor_occupied=0.9)
@@ -34,7 +39,7 @@ def build_pair(pyoracle, size, levels=3):
     return world, orc, rep
 
 
-def test_config3_stream_40hz_4096(hsb_lib, pyoracle):
+def test_config3_stream_40hz_4096(hsb_lib, pyoracle, oracle_kinds):
     import ctypes as C
 
     from hector_slam_b200 import synth
@@ -45,7 +50,7 @@ def test_config3_stream_40hz_4096(hsb_lib, pyoracle):
     L = host(hsb_lib)
     p = L.hsbp_create(0.05, size, size, 0.5, 0.5, 3, 0)
     assert p
-    orc = pyoracle.Oracle("port", 0.05, size, 3)
+    orc = pyoracle.Oracle(best_kind(oracle_kinds), 0.05, size, 3)
     L.hsbp_set_update_factors(p, 0.4, 0.9)
     orc.set_update_factors(0.4, 0.9)
     # node defaults: write the map after 0.4 m or 0.9 rad (hector_mapping/src/HectorMappingRos.cpp:75-76)
@@ -76,7 +81,7 @@ def test_config3_stream_40hz_4096(hsb_lib, pyoracle):
         pose = pose + np.array([0.0125 * np.cos(heading), 0.0125 * np.sin(heading), 0.0075])
     lat = np.sort(np.asarray(lat[5:])) * 1e3
     p50, p99 = lat[len(lat) // 2], lat[int(0.99 * len(lat))]
-    print(f"config 3: {n_scans} scans, worst pose diff {worst:.2e}; update() latency p50 {p50:.3f} ms p99 {p99:.3f} ms "
+    report(f"config 3 ({orc.kind} oracle): {n_scans} scans, worst pose diff {worst:.2e}; update() latency p50 {p50:.3f} ms p99 {p99:.3f} ms "
           f"(budget 25 ms) -> {1e3 / lat.mean():.0f} scans/s sustained")
     assert p99 < 25.0
     assert np.abs(np.asarray(out[:2], np.float64) - (pose[:2] - 0.0125 * np.array([np.cos(heading), np.sin(heading)]))).max() < 0.05
@@ -84,10 +89,10 @@ def test_config3_stream_40hz_4096(hsb_lib, pyoracle):
     orc.close()
 
 
-def test_config4_relocalisation_65536_hypotheses(hsb_lib, pyoracle):
+def test_config4_relocalisation_65536_hypotheses(hsb_lib, pyoracle, oracle_kinds):
     from hector_slam_b200 import synth
 
-    world, orc, rep = build_pair(pyoracle, 4096)
+    world, orc, rep = build_pair(pyoracle, 4096, kind=best_kind(oracle_kinds))
     rng = np.random.default_rng(2)
     truth = world.sample_free_poses(1, rng, margin=1.0)[0]
     scan = synth.make_scan(world, truth, np.random.default_rng(7))
@@ -114,7 +119,7 @@ def test_config4_relocalisation_65536_hypotheses(hsb_lib, pyoracle):
     want, _, _ = orc.match_batch(hyp[idx], np.tile(scan, (idx.size, 1)), offs, nthreads=8)
     conv = np.abs(want[:, :2] - truth[:2]).max(axis=1) < 0.5   # oracle itself converged (Q4: count the rest)
     ex, ey, ea = pose_err(got[idx][conv], want[conv])
-    print(f"config 4: {B} hypotheses in {dt * 1e3:.1f} ms host-to-host; in-basin {idx.size}, oracle converged {conv.sum()}, "
+    report(f"config 4 ({orc.kind} oracle): {B} hypotheses in {dt * 1e3:.1f} ms host-to-host; in-basin {idx.size}, oracle converged {conv.sum()}, "
           f"max diff {max(ex, ey, ea):.2e}; all hypotheses within 2 cm of truth: {(np.abs(got[:, :2] - truth[:2]).max(axis=1) < 0.02).sum()}")
     assert conv.mean() > 0.95
     assert max(ex, ey) <= 1e-4 and ea <= 1e-4
@@ -125,10 +130,10 @@ def test_config4_relocalisation_65536_hypotheses(hsb_lib, pyoracle):
     orc.close()
 
 
-def test_config5_replay_8192(hsb_lib, pyoracle):
+def test_config5_replay_8192(hsb_lib, pyoracle, oracle_kinds):
     from hector_slam_b200 import parallel, synth
 
-    world, orc, rep = build_pair(pyoracle, 8192)
+    world, orc, rep = build_pair(pyoracle, 8192, kind=best_kind(oracle_kinds))
     rng = np.random.default_rng(11)
     B = 1536
     poses = world.sample_free_poses(B, rng)               # spread over all 64 rooms
@@ -140,7 +145,7 @@ def test_config5_replay_8192(hsb_lib, pyoracle):
     want, _, _ = orc.match_batch(h, p, o, nthreads=8)
     ok = np.abs(want[:, :2] - h[:, :2]).max(axis=1) < 0.5
     ex, ey, ea = pose_err(got[ok], want[ok])
-    print(f"config 5: shard [{lo},{hi}) of {B} scans on the 8192^2 map, oracle diverged on {(~ok).sum()}, max diff {max(ex, ey, ea):.2e}")
+    report(f"config 5 ({orc.kind} oracle): shard [{lo},{hi}) of {B} scans on the 8192^2 map, oracle diverged on {(~ok).sum()}, max diff {max(ex, ey, ea):.2e}")
     assert ok.mean() > 0.97 and max(ex, ey) <= 1e-4 and ea <= 1e-4
     assert np.abs(got[ok][:, :2] - poses[lo:hi][ok][:, :2]).max() < 0.03
     rep.close()

@@ -6,7 +6,7 @@ import subprocess
 
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, report
 
 pytestmark = pytest.mark.gpu
 BIN = os.path.join(ROOT, "oracle", "_ref", "dropin_check")
@@ -17,4 +17,7 @@ def test_reference_facade_with_b200_maprep(hsb_lib):
         pytest.skip("oracle/_ref/dropin_check not built (needs /root/reference at build time)")
     out = subprocess.run([BIN, "60"], capture_output=True, text=True, timeout=300)
     print(out.stdout, out.stderr)
+    for line in out.stdout.splitlines():
+        if 'cells touched' in line or 'max' in line:
+            report('dropin_check: ' + line)
     assert out.returncode == 0 and "DROPIN OK" in out.stdout, out.stdout + out.stderr

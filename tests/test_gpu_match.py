@@ -8,7 +8,7 @@ matcher on identical scans and maps.  Per-evaluation H / dTr: relative 1e-4 of t
 import numpy as np
 import pytest
 
-from conftest import golden_planes, load_golden, pose_err
+from conftest import golden_planes, load_golden, pose_err, report
 
 pytestmark = pytest.mark.gpu
 
@@ -293,6 +293,7 @@ def test_non_square_map_other_resolution_and_start(hsb_lib, pyoracle, oracle_kin
         rep.onMapUpdated()
     for l in range(2):
         d = np.abs(rep.download_level(l) - orc.get_logodds(l))
+        report(f"planes[non-square level {l}, mode {mode}]: {int((d > 1e-5).sum())} cells differ of {int((orc.get_logodds(l) != 0).sum())} touched")
         assert (d > 1e-5).sum() <= max(3, int(5e-4 * (d.size))), (l, int((d > 1e-5).sum()))
         rep.upload_level(l, orc.get_logodds(l))      # continue from identical planes
     test_poses = world.sample_free_poses(64, rng, margin=0.8)

@@ -6,7 +6,7 @@ differs (a beam end rounding into a neighbouring cell) must be tiny and is repor
 import numpy as np
 import pytest
 
-from conftest import apply_diff, golden_planes, load_golden, pose_err
+from conftest import apply_diff, golden_planes, load_golden, pose_err, report
 
 pytestmark = pytest.mark.gpu
 
@@ -18,6 +18,7 @@ def compare_planes(got, want, what, max_bad_frac=2e-4):
     bad = diff > PLANE_TOL
     touched = max(1, int((want != 0).sum()))
     frac = bad.sum() / touched
+    report(f"planes[{what}]: {int(bad.sum())} cells differ by > {PLANE_TOL} of {touched} touched (max |diff| {float(diff.max()):.3e})")
     assert frac <= max_bad_frac, (what, int(bad.sum()), touched, float(diff.max()))
     return int(bad.sum())
 
