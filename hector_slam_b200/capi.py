@@ -31,6 +31,7 @@ EXPORTED = [
     "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch",
     "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device", "hsb_raycast_batch",
     "hsb_read_trace", "hsb_get_last_launch_shape",
+    "hsb_covariance_batch", "hsb_get_map_origin", "hsb_get_dist_batch", "hsb_set_cloud_format", "hsb_cloud_to_points", "hsb_match_batch_cloud", "hsb_match_batch_cloud_device",
 ]
 
 
@@ -54,6 +55,11 @@ class HsbConfig(C.Structure):
 class HsbScanFormat(C.Structure):
     _fields_ = [("n_beams", C.c_int), ("angle_min", C.c_float), ("angle_increment", C.c_float),
                 ("range_min", C.c_float), ("range_max", C.c_float)]
+
+
+class HsbCloudFormat(C.Structure):
+    _fields_ = [("laser_transform", C.c_double * 12), ("sqr_laser_min_dist", C.c_float), ("sqr_laser_max_dist", C.c_float),
+                ("laser_z_min_value", C.c_float), ("laser_z_max_value", C.c_float)]
 
 
 class HsbError(RuntimeError):
@@ -121,8 +127,15 @@ def load_library() -> C.CDLL:
     sig("hsb_match_batch_ranges_device", i, vp, i, vp, vp, vp, vp, vp)
     sig("hsb_download_occupancy", i, vp, i, vp)
     sig("hsb_likelihood_batch", i, vp, i, i, vp, vp, vp, i, vp)
+    sig("hsb_covariance_batch", i, vp, i, i, vp, vp, vp, i, vp, vp)
+    sig("hsb_get_map_origin", i, vp, i, vp)
+    sig("hsb_get_dist_batch", i, vp, i, i, vp, vp, vp, vp, vp)
     sig("hsb_get_dirty_rect", i, vp, i, vp, i)
     sig("hsb_raycast_batch", i, vp, i, i, vp, vp, vp, vp)
+    sig("hsb_set_cloud_format", i, vp, C.POINTER(HsbCloudFormat))
+    sig("hsb_cloud_to_points", i, vp, vp, i, vp, ip, vp)
+    sig("hsb_match_batch_cloud", i, vp, i, vp, vp, vp, vp, vp, vp, vp)
+    sig("hsb_match_batch_cloud_device", i, vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp)
     sig("hsb_read_trace", i, vp, vp, i)
     sig("hsb_get_last_launch_shape", i, vp, vp)
     sig("hsb_pack_rect_device", i, vp, i, vp, vp, vp)
@@ -385,6 +398,50 @@ class MapRepB200:
         self._check(self.lib.hsb_match_batch_ranges_device(self.h, int(B), d_hints, d_ranges, d_out_poses, d_out_cov,
                                                            stream))
 
+    # -- point clouds in (rosPointCloudToDataContainer fused into the match kernel) -----------------
+    def set_cloud_format(self, laser_transform, sqr_laser_min_dist: float, sqr_laser_max_dist: float,
+                         laser_z_min_value: float, laser_z_max_value: float):
+        fmt = HsbCloudFormat()
+        for k, v in enumerate(np.asarray(laser_transform, np.float64).reshape(12)):
+            fmt.laser_transform[k] = float(v)
+        fmt.sqr_laser_min_dist, fmt.sqr_laser_max_dist = float(sqr_laser_min_dist), float(sqr_laser_max_dist)
+        fmt.laser_z_min_value, fmt.laser_z_max_value = float(laser_z_min_value), float(laser_z_max_value)
+        self._check(self.lib.hsb_set_cloud_format(self.h, C.byref(fmt)))
+
+    def cloud_to_points(self, points_xyz):
+        """-> (endpoints (k, 2) float32, origo (2,) float32)"""
+        p = _f32(points_xyz).reshape(-1, 3)
+        out = np.zeros((max(1, p.shape[0]), 2), np.float32)
+        origo = np.zeros(2, np.float32)
+        n = C.c_int()
+        self._check(self.lib.hsb_cloud_to_points(self.h, p.ctypes.data if p.size else None, p.shape[0], out.ctypes.data,
+                                                 C.byref(n), origo.ctypes.data))
+        return out[: n.value].copy(), origo
+
+    def match_batch_cloud(self, hints, points_xyz, offsets, transforms=None, want_cov: bool = True):
+        """-> (poses (B, 3), cov (B, 3, 3) | None, origo (B, 2))"""
+        B = int(hints.shape[0])
+        if isinstance(hints, np.ndarray):
+            hints = _f32(hints).reshape(-1, 3)
+        if isinstance(points_xyz, np.ndarray):
+            points_xyz = _f32(points_xyz).reshape(-1, 3)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        if transforms is not None:
+            transforms = np.ascontiguousarray(transforms, dtype=np.float64).reshape(B, 12)
+        poses = np.zeros((B, 3), np.float32)
+        cov = np.zeros((B, 9), np.float32) if want_cov else None
+        origo = np.zeros((B, 2), np.float32)
+        self._check(self.lib.hsb_match_batch_cloud(self.h, B, _ptr(hints), _ptr(points_xyz), offsets.ctypes.data,
+                                                   _ptr(transforms), poses.ctypes.data, _ptr(cov), origo.ctypes.data))
+        return poses, (cov.reshape(B, 3, 3) if want_cov else None), origo
+
+    def match_batch_cloud_device(self, B: int, d_hints: int, d_points_xyz: int, d_offsets: int, max_points_per_scan: int,
+                                 d_transforms: int | None, d_out_poses: int, d_out_cov: int | None,
+                                 d_out_origo: int | None, stream: int = 0):
+        self._check(self.lib.hsb_match_batch_cloud_device(self.h, int(B), d_hints, d_points_xyz, d_offsets,
+                                                          int(max_points_per_scan), d_transforms, d_out_poses, d_out_cov,
+                                                          d_out_origo, stream))
+
     # -- planes ----------------------------------------------------------------------------------
     def upload_level(self, level: int, logodds):
         sx, sy, _ = self.level_info(level)
@@ -428,6 +485,22 @@ class MapRepB200:
                                                   offp, n_shared, out.ctypes.data))
         return out
 
+    def covariance_batch(self, level: int, poses_world, points_xy, offsets=None):
+        """getCovarianceForPose (+ getCovMatrixWorldCoords) for B world poses. -> (cov_map (B,3,3), cov_world (B,3,3))"""
+        poses = _f32(poses_world).reshape(-1, 3)
+        pts = _f32(points_xy).reshape(-1, 2)
+        B = poses.shape[0]
+        n_shared, offp = 0, None
+        if offsets is None:
+            n_shared = pts.shape[0]
+        else:
+            offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+            offp = offsets.ctypes.data
+        cm, cw = np.zeros((B, 9), np.float32), np.zeros((B, 9), np.float32)
+        self._check(self.lib.hsb_covariance_batch(self.h, level, B, poses.ctypes.data, pts.ctypes.data if pts.size else None,
+                                                  offp, n_shared, cm.ctypes.data, cw.ctypes.data))
+        return cm.reshape(B, 3, 3), cw.reshape(B, 3, 3)
+
     def raycast_batch(self, level: int, begin_cells, end_cells):
         """checkOccupancyBresenhami for B rays. -> (dist (B,) float32 [-1 = no hit], hit (B,2) int32)"""
         b = np.ascontiguousarray(begin_cells, dtype=np.int32).reshape(-1, 2)
@@ -438,6 +511,22 @@ class MapRepB200:
         self._check(self.lib.hsb_raycast_batch(self.h, level, B, b.ctypes.data, e.ctypes.data, dist.ctypes.data,
                                                hit.ctypes.data))
         return dist, hit
+
+    def map_origin(self, level: int) -> np.ndarray:
+        out = np.zeros(2, np.float32)
+        self._check(self.lib.hsb_get_map_origin(self.h, level, out.ctypes.data))
+        return out
+
+    def get_dist_batch(self, level: int, begin_world, end_world):
+        """DistanceMeasurementProvider::getDist for B world-frame rays.
+        -> (dist [m] (B,), hit_world (B, 2), found (B,) bool)"""
+        b = _f32(begin_world).reshape(-1, 2)
+        e = _f32(end_world).reshape(-1, 2)
+        B = b.shape[0]
+        dist, hit, found = np.zeros(B, np.float32), np.zeros((B, 2), np.float32), np.zeros(B, np.int32)
+        self._check(self.lib.hsb_get_dist_batch(self.h, level, B, b.ctypes.data, e.ctypes.data, dist.ctypes.data,
+                                                hit.ctypes.data, found.ctypes.data))
+        return dist, hit, found.astype(bool)
 
     def get_dirty_rect(self, level: int, reset: bool = False):
         """(x0, y0, x1, y1) inclusive of the cells written since the last reset, or None."""

@@ -62,6 +62,9 @@ struct hsb_handle {
   DevBuf d_beam_cs, d_ranges, d_occ;
   hsb_scan_format fmt = hsb_scan_format();
   bool fmt_set = false;
+  hsb_cloud_format cfmt = hsb_cloud_format();
+  bool cfmt_set = false;
+  DevBuf d_cloud, d_cloud_off, d_cloud_tf, d_origo;
   int last_n = 0;
   float last_origo[2] = {0.f, 0.f};
   // pinned host scratch
@@ -72,7 +75,7 @@ struct hsb_handle {
   DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
   float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0;
   DevBuf d_trace;
   int trace_scans = 0;
   int last_shape[6] = {0, 0, 0, 0, 0, 0};  // W, G, U, staged points per scan (0 = none), grid, resident CTAs / SM
@@ -202,14 +205,13 @@ void fill_level_dev(const hsb_handle* h, int l, HsbLevelDev& d) {
 // ---- match launch -----------------------------------------------------------------------------
 template <int W, int G, int MODE, int U, bool PACK>
 int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
-  size_t header = hsb::MatchSmem<W, G>::kHeaderBytes;
+  const size_t header = hsb::MatchSmem<W, G>::kHeaderBytes;
   auto kern = hsb::match_kernel<W, G, MODE, U, PACK>;
+  constexpr size_t kMaxDyn = 232448;   // dynamic shared memory one CTA may ask for (227 KB)
+  constexpr int gt = W * 32;           // threads per scan
   int cap = 0;
-  if (h->tune_stage_smem || P.ranges) {
-    cap = ((max_n + 1) + 1) & ~1;  // n + head padding, even
-    if (header + (size_t)G * cap * 8 > 200 * 1024) cap = 0;
-  }
-  if (P.ranges && cap == 0) return fail(h, HSB_ERR_UNSUPPORTED, "scan too long for the fused range conversion (%d beams)", max_n);
+  const bool fused = P.ranges || P.cloud;   // conversion fused into the staging step: the whole scan must be staged
+  if (h->tune_stage_smem || fused) cap = ((max_n + 1) + 1) & ~1;  // n + head padding, even
   // resident CTAs per SM for a given dynamic shared-memory size: block, thread, register and
   // shared-memory limits (1 KB per CTA is reserved by the driver)
   static int regs = 0;
@@ -222,31 +224,35 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
   auto resident = [&](size_t smem_bytes) {
     int blocks = std::min(32, 2048 / threads);
     blocks = std::min(blocks, 65536 / (((regs + 7) / 8 * 8) * threads));
-    blocks = std::min<long>(blocks, (long)(232448 / (smem_bytes + 1024)));
+    blocks = std::min<long>(blocks, (long)(kMaxDyn / (smem_bytes + 1024)));
     return std::max(blocks, 1);
   };
-  if (cap > 0 && !P.ranges && h->tune_stage_smem == 1) {
+  // slots (a multiple of the group size, + 2 for the alignment head) that fit when `ctas` CTAs share an SM
+  auto cap_for = [&](long ctas) {
+    const long budget = std::min<long>((long)kMaxDyn, (long)kMaxDyn / ctas - 1024) - (long)header;
+    int pts = (int)(budget / 8 / G);
+    pts = (pts - 2) / gt * gt;
+    return pts >= 4 * gt ? pts + 2 : 0;
+  };
+  const bool may_split = h->tune_partial && !PACK && !fused;   // a staged PREFIX is allowed
+  if (cap > 0 && header + (size_t)G * cap * 8 > kMaxDyn) {        // the CTA's scans do not fit whole
+    if (fused) return fail(h, HSB_ERR_UNSUPPORTED, "scan too long for the fused conversion (%d points)", max_n);
+    cap = may_split ? cap_for(1) : 0;
+  }
+  if (cap > 0 && !fused && h->tune_stage_smem == 1) {
     // Wave quantisation (profiles/r01_sweep_large_batches.log): staging costs ~9 KB of shared memory
     // per scan, i.e. fewer resident groups.  If the batch does not fit the resident groups WITH the
-    // whole scan staged but does fit WITHOUT (one wave instead of one and a bit), stage only the prefix
+    // scans staged but does fit WITHOUT (one wave instead of one and a bit), stage only the prefix
     // of each scan that the shared memory of a one-wave residency affords and read the rest through
-    // L1 (tuning "partial" = 0: stage nothing in that case, the round-1 behaviour).
+    // L1 (tuning "partial" = 0: stage nothing in that case).
     const long groups = ((long)P.B + G - 1) / G;
     const long slots_staged = (long)resident(header + (size_t)G * cap * 8) * h->sm_count;
     const long slots_plain = (long)resident(header) * h->sm_count;
-    if (groups > slots_staged && groups <= slots_plain) {
-      cap = 0;
-      if (h->tune_partial && !PACK) {
-        const long need = (groups + h->sm_count - 1) / h->sm_count;       // CTAs per SM for one wave
-        const long budget = 232448 / need - 1024 - (long)header;          // bytes of points per CTA
-        const int gt = W * 32;
-        int pts = (int)(budget / 8 / G);
-        pts = (pts - 2) / gt * gt;
-        if (pts >= 4 * gt) cap = pts + 2;
-      }
-    }
+    if (groups > slots_staged && groups <= slots_plain)
+      cap = may_split ? cap_for((groups + h->sm_count - 1) / h->sm_count) : 0;
   }
   P.prefetch = h->tune_prefetch;
+  P.pace_slack = h->tune_pace;
   P.pts_cap = cap;
   size_t smem = header + (size_t)G * cap * 8;
   if (smem > 48 * 1024) {
@@ -297,6 +303,10 @@ int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t 
   HSB_CASE(4, 1, 4);
   HSB_CASE(8, 1, 4);
   HSB_CASE(16, 1, 4);
+  // many one-warp scans per CTA, paced (see match_kernel): 4 / 2 / 1 CTAs per SM
+  HSB_CASE(1, 7, 4);
+  HSB_CASE(1, 14, 4);
+  HSB_CASE(1, 28, 4);
   // deeper gather batches: the whole per-lane share of a 1081-point scan in flight at once
   HSB_CASE(1, 1, 8);
   HSB_CASE(2, 1, 8);
@@ -547,7 +557,8 @@ int hsb_destroy(hsb_handle* h) {
   cudaDeviceSynchronize();
   for (int l = 0; l < HSB_MAX_LEVELS; ++l) destroy_level(h, h->lv[l]);
   DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_gate, &h->d_last_pts, &h->d_upd_pts,
-                    &h->d_beam_cs, &h->d_ranges, &h->d_occ, &h->d_trace};
+                    &h->d_beam_cs, &h->d_ranges, &h->d_occ, &h->d_trace,
+                    &h->d_cloud, &h->d_cloud_off, &h->d_cloud_tf, &h->d_origo};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -641,6 +652,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "partial")) h->tune_partial = value;
   else if (!strcmp(key, "prefetch")) h->tune_prefetch = value;
   else if (!strcmp(key, "trace")) h->tune_trace = value;
+  else if (!strcmp(key, "pace")) h->tune_pace = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }
@@ -928,6 +940,139 @@ int hsb_match_batch_ranges(hsb_handle* h, int B, const float* hints, const float
   return HSB_OK;
 }
 
+// ---- point clouds (N2, the node's default input) ------------------------------------------------
+
+int hsb_set_cloud_format(hsb_handle* h, const hsb_cloud_format* fmt) {
+  if (!h || !fmt) return HSB_ERR_INVALID_ARG;
+  for (int i = 0; i < 12; ++i)
+    if (!std::isfinite(fmt->laser_transform[i])) return fail(h, HSB_ERR_INVALID_ARG, "laser_transform is not finite");
+  h->cfmt = *fmt;
+  h->cfmt_set = true;
+  return HSB_OK;
+}
+
+static void fill_cloud_params(const hsb_handle* h, HsbMatchParams& P, const float* d_cloud, const int* d_offsets,
+                              const double* d_transforms, float* d_origo) {
+  P.cloud = d_cloud;
+  P.cloud_offsets = d_offsets;
+  P.cloud_tf = d_transforms;
+  memcpy(P.cloud_tf0, h->cfmt.laser_transform, sizeof(P.cloud_tf0));
+  P.sqr_min_dist = h->cfmt.sqr_laser_min_dist;
+  P.sqr_max_dist = h->cfmt.sqr_laser_max_dist;
+  P.z_min = h->cfmt.laser_z_min_value;
+  P.z_max = h->cfmt.laser_z_max_value;
+  P.scale_to_map = h->lv[0].scale;
+  P.out_origo = d_origo;
+}
+
+int hsb_cloud_to_points(hsb_handle* h, const float* points_xyz, int n, float* out_xy, int* out_n, float out_origo[2]) {
+  if (!h || n < 0 || (n > 0 && !points_xyz) || !out_xy || !out_n) return HSB_ERR_INVALID_ARG;
+  if (!h->cfmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_cloud_format has not been called");
+  DeviceGuard guard(h->device);
+  int s;
+  if ((s = ensure(h, h->d_cloud, (size_t)(n > 0 ? n : 1) * 12)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_pts, (size_t)(n > 0 ? n : 1) * 8 + 16)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_cloud_tf, 12 * sizeof(double))) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_scratch, 64 * sizeof(float))) != HSB_OK) return s;
+  cudaStream_t st = h->stream;
+  if (n > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_cloud.p, points_xyz, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+  HSB_CUDA(h, cudaMemcpyAsync(h->d_cloud_tf.p, h->cfmt.laser_transform, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+  int* d_n = reinterpret_cast<int*>(static_cast<float*>(h->d_scratch.p) + 48);
+  hsb::cloud_to_points_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(h->d_cloud.p), n, static_cast<const double*>(h->d_cloud_tf.p),
+                                                 h->cfmt.sqr_laser_min_dist, h->cfmt.sqr_laser_max_dist, h->cfmt.laser_z_min_value,
+                                                 h->cfmt.laser_z_max_value, h->lv[0].scale, static_cast<float2*>(h->d_pts.p), d_n);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 48, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  const int kept = *reinterpret_cast<int*>(h->h_pin + 48);
+  if (kept > 0) HSB_CUDA(h, cudaMemcpy(out_xy, h->d_pts.p, (size_t)kept * 8, cudaMemcpyDeviceToHost));
+  *out_n = kept;
+  if (out_origo) {   // HectorMappingRos.cpp:516-517: Vector2f(laserPos.x(), laserPos.y()) * scaleToMap (host fp32, no contraction)
+    volatile float ox = (float)h->cfmt.laser_transform[3], oy = (float)h->cfmt.laser_transform[7];
+    volatile float sx = ox * h->lv[0].scale, sy = oy * h->lv[0].scale;
+    out_origo[0] = sx;
+    out_origo[1] = sy;
+  }
+  return HSB_OK;
+}
+
+int hsb_match_batch_cloud_device(hsb_handle* h, int B, const float* d_hints, const float* d_points_xyz, const int* d_offsets,
+                                 int max_points_per_scan, const double* d_transforms, float* d_out_poses, float* d_out_cov,
+                                 float* d_out_origo, void* stream) {
+  if (!h || B < 0 || !d_hints || !d_offsets || !d_out_poses || max_points_per_scan < 0) return HSB_ERR_INVALID_ARG;
+  if (!h->cfmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_cloud_format has not been called");
+  if (B == 0) return HSB_OK;
+  if (!d_points_xyz && max_points_per_scan > 0) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  DeviceGuard guard(h->device);
+  HsbMatchParams P;
+  fill_match_params(h, P);
+  P.B = B;
+  P.hints = d_hints;
+  P.out_poses = d_out_poses;
+  P.out_cov = d_out_cov;
+  fill_cloud_params(h, P, d_points_xyz, d_offsets, d_transforms, d_out_origo);
+  return launch_match(h, P, max_points_per_scan, (cudaStream_t)stream);
+}
+
+int hsb_match_batch_cloud(hsb_handle* h, int B, const float* hints, const float* points_xyz, const int* offsets,
+                          const double* transforms, float* out_poses, float* out_cov, float* out_origo) {
+  if (!h || B < 0 || !hints || !offsets || !out_poses) return HSB_ERR_INVALID_ARG;
+  if (!h->cfmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_cloud_format has not been called");
+  if (B == 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  int max_n = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = offsets[b + 1] - offsets[b];
+    if (n < 0) return fail(h, HSB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    max_n = std::max(max_n, n);
+  }
+  const size_t total = (size_t)offsets[B] - (size_t)offsets[0];
+  if (total > 0 && !points_xyz) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  int s;
+  if ((s = ensure(h, h->d_hints, (size_t)B * 12)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_cloud, ((size_t)offsets[B] + 1) * 12)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_cloud_off, (size_t)(B + 1) * 4)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_poses, (size_t)B * 12)) != HSB_OK) return s;
+  if (out_cov && (s = ensure(h, h->d_cov, (size_t)B * 36)) != HSB_OK) return s;
+  if (out_origo && (s = ensure(h, h->d_origo, (size_t)B * 8)) != HSB_OK) return s;
+  if (transforms && (s = ensure(h, h->d_cloud_tf, (size_t)B * 12 * sizeof(double))) != HSB_OK) return s;
+  float* d_hints = static_cast<float*>(h->d_hints.p);
+  float* d_cloud = static_cast<float*>(h->d_cloud.p);
+  int* d_off = static_cast<int*>(h->d_cloud_off.p);
+  float* d_poses = static_cast<float*>(h->d_poses.p);
+  float* d_cov = out_cov ? static_cast<float*>(h->d_cov.p) : nullptr;
+  float* d_origo = out_origo ? static_cast<float*>(h->d_origo.p) : nullptr;
+  double* d_tf = transforms ? static_cast<double*>(h->d_cloud_tf.p) : nullptr;
+  // same copy/compute pipeline as hsb_match_batch: chunk c's points travel while chunk c-1 is matched
+  const std::vector<int> bounds = pipeline_bounds(B, h->tune_chunk);
+  ShapeScope shape_scope(h, B, bounds.size() - 1);
+  cudaStream_t s0 = h->copy_stream[0];
+  HSB_CUDA(h, cudaMemcpyAsync(d_off, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s0));
+  HSB_CUDA(h, cudaMemcpyAsync(d_hints, hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
+  if (d_tf) HSB_CUDA(h, cudaMemcpyAsync(d_tf, transforms, (size_t)B * 12 * sizeof(double), cudaMemcpyHostToDevice, s0));
+  HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
+  HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
+  for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
+    const int b0 = bounds[ci], b1 = bounds[ci + 1];
+    cudaStream_t st = h->copy_stream[ci & 1];
+    const size_t p0 = (size_t)offsets[b0], p1 = (size_t)offsets[b1];
+    if (p1 > p0) HSB_CUDA(h, cudaMemcpyAsync(d_cloud + 3 * p0, points_xyz + 3 * p0, (p1 - p0) * 12, cudaMemcpyHostToDevice, st));
+    s = hsb_match_batch_cloud_device(h, b1 - b0, d_hints + 3 * (size_t)b0, d_cloud, d_off + b0, max_n, d_tf ? d_tf + 12 * (size_t)b0 : nullptr,
+                                     d_poses + 3 * (size_t)b0, d_cov ? d_cov + 9 * (size_t)b0 : nullptr,
+                                     d_origo ? d_origo + 2 * (size_t)b0 : nullptr, st);
+    if (s != HSB_OK) return s;
+    HSB_CUDA(h, cudaMemcpyAsync(out_poses + 3 * (size_t)b0, d_poses + 3 * (size_t)b0, (size_t)(b1 - b0) * 12, cudaMemcpyDeviceToHost, st));
+    if (out_cov)
+      HSB_CUDA(h, cudaMemcpyAsync(out_cov + 9 * (size_t)b0, d_cov + 9 * (size_t)b0, (size_t)(b1 - b0) * 36, cudaMemcpyDeviceToHost, st));
+    if (out_origo)
+      HSB_CUDA(h, cudaMemcpyAsync(out_origo + 2 * (size_t)b0, d_origo + 2 * (size_t)b0, (size_t)(b1 - b0) * 8, cudaMemcpyDeviceToHost, st));
+  }
+  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[0]));
+  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[1]));
+  return HSB_OK;
+}
+
 // ---- map writing -------------------------------------------------------------------------------
 
 static int run_update(hsb_handle* h, HsbUpdateParams& P, int max_n) {
@@ -1208,6 +1353,44 @@ int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses, co
   return HSB_OK;
 }
 
+int hsb_covariance_batch(hsb_handle* h, int level, int B, const float* poses, const float* pts, const int* offsets, int n_shared,
+                         float* out_cov_map, float* out_cov_world) {
+  if (!h || level < 0 || level >= h->levels || B < 0 || !poses || (!out_cov_map && !out_cov_world)) return HSB_ERR_INVALID_ARG;
+  if (B == 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  size_t total = offsets ? (size_t)offsets[B] : (size_t)(n_shared > 0 ? n_shared : 0);
+  if (total > 0 && !pts) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  int s;
+  if ((s = ensure(h, h->d_hints, (size_t)B * 12)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_pts, total * 8 + 16)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_offsets, (size_t)(B + 1) * 4)) != HSB_OK) return s;
+  if ((s = ensure(h, h->d_cov, (size_t)B * 72)) != HSB_OK) return s;
+  cudaStream_t st = h->stream;
+  HSB_CUDA(h, cudaMemcpyAsync(h->d_hints.p, poses, (size_t)B * 12, cudaMemcpyHostToDevice, st));
+  if (total > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_pts.p, pts, total * 8, cudaMemcpyHostToDevice, st));
+  if (offsets) HSB_CUDA(h, cudaMemcpyAsync(h->d_offsets.p, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
+  HsbLevelDev L;
+  fill_level_dev(h, level, L);
+  const int blocks = std::min(B, h->sm_count * 8);
+  const int* d_off = offsets ? static_cast<const int*>(h->d_offsets.p) : nullptr;
+  float* d_map = static_cast<float*>(h->d_cov.p);
+  float* d_world = d_map + 9 * (size_t)B;
+  if (h->gather_mode == HSB_GATHER_TEX)
+    hsb::covariance_kernel<hsb::MODE_TEX><<<blocks, 224, 0, st>>>(L, B, static_cast<const float*>(h->d_hints.p),
+                                                                  static_cast<const float2*>(h->d_pts.p), d_off,
+                                                                  offsets ? 0 : n_shared, h->lv[level].cell_length, d_map, d_world);
+  else
+    hsb::covariance_kernel<hsb::MODE_LDG><<<blocks, 224, 0, st>>>(L, B, static_cast<const float*>(h->d_hints.p),
+                                                                  static_cast<const float2*>(h->d_pts.p), d_off,
+                                                                  offsets ? 0 : n_shared, h->lv[level].cell_length, d_map, d_world);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  if (out_cov_map) HSB_CUDA(h, cudaMemcpyAsync(out_cov_map, d_map, (size_t)B * 36, cudaMemcpyDeviceToHost, st));
+  if (out_cov_world) HSB_CUDA(h, cudaMemcpyAsync(out_cov_world, d_world, (size_t)B * 36, cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  return HSB_OK;
+}
+
 int hsb_get_dirty_rect(hsb_handle* h, int level, int rect[4], int reset) {
   if (!h || level < 0 || level >= h->levels || !rect) return HSB_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
@@ -1281,6 +1464,50 @@ int hsb_raycast_batch(hsb_handle* h, int level, int B, const int* begin_cells, c
   HSB_CUDA(h, cudaGetLastError());
   HSB_CUDA(h, cudaMemcpyAsync(out_dist, d_dist, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (out_hit) HSB_CUDA(h, cudaMemcpyAsync(out_hit, d_hit, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  HSB_CUDA(h, cudaStreamSynchronize(st));
+  return HSB_OK;
+}
+
+int hsb_get_map_origin(const hsb_handle* h, int level, float out[2]) {
+  if (!h || level < 0 || level >= h->levels || !out) return HSB_ERR_INVALID_ARG;
+  // HectorMappingRos::setServiceGetMapData (HectorMappingRos.cpp:546-550): getWorldCoords(0, 0) - cellLength * 0.5f
+  float wx, wy;
+  affine_apply_host(h->lv[level].wtm, 0.0f, 0.0f, &wx, &wy);
+  volatile float half = h->lv[level].cell_length * 0.5f;
+  volatile float ox = wx - half, oy = wy - half;
+  out[0] = ox;
+  out[1] = oy;
+  return HSB_OK;
+}
+
+int hsb_get_dist_batch(hsb_handle* h, int level, int B, const float* begin_world, const float* end_world, float* out_dist,
+                       float* out_hit_world, int* out_found) {
+  if (!h || level < 0 || level >= h->levels || B < 0 || !begin_world || !end_world || !out_dist) return HSB_ERR_INVALID_ARG;
+  if (B == 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  int s;
+  if ((s = ensure(h, h->d_pts, (size_t)B * 16 + 16)) != HSB_OK) return s;      // begin | end
+  if ((s = ensure(h, h->d_poses, (size_t)B * 16 + 16)) != HSB_OK) return s;    // dist | hit (2) | found
+  cudaStream_t st = h->stream;
+  float2* d_begin = static_cast<float2*>(h->d_pts.p);
+  float2* d_end = d_begin + B;
+  float2* d_hit = static_cast<float2*>(h->d_poses.p);
+  float* d_dist = reinterpret_cast<float*>(d_hit + B);
+  int* d_found = reinterpret_cast<int*>(d_dist + B);
+  HSB_CUDA(h, cudaMemcpyAsync(d_begin, begin_world, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  HSB_CUDA(h, cudaMemcpyAsync(d_end, end_world, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  float origo[2];
+  hsb_get_map_origin(h, level, origo);
+  volatile float inv_scale = 1.0f / L.cell_length;   // CoordinateTransformer::setTransforms, HectorMapTools.h:64
+  int blocks = std::min((B + 7) / 8, h->sm_count * 8);
+  hsb::getdist_kernel<<<blocks, 256, 0, st>>>(L.logodds, L.sx, L.sy, B, origo[0], origo[1], L.cell_length, inv_scale, d_begin, d_end,
+                                              d_dist, out_hit_world ? d_hit : nullptr, out_found ? d_found : nullptr);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  HSB_CUDA(h, cudaMemcpyAsync(out_dist, d_dist, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (out_hit_world) HSB_CUDA(h, cudaMemcpyAsync(out_hit_world, d_hit, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  if (out_found) HSB_CUDA(h, cudaMemcpyAsync(out_found, d_found, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   HSB_CUDA(h, cudaStreamSynchronize(st));
   return HSB_OK;
 }

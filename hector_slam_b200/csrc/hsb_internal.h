@@ -39,7 +39,17 @@ struct HsbMatchParams {
   int n_beams;
   float range_min, range_max_c;  // keep range_min < r < range_max - 0.1
   float scale_to_map;
+  // point-cloud input (N2, the node's default path: rosPointCloudToDataContainer fused into the staging step);
+  // cloud == nullptr selects one of the inputs above.  Scan b is the Point32 triples cloud[3*cloud_offsets[b] ..
+  // 3*cloud_offsets[b+1]); its laser transform is cloud_tf + 12*b (rows of [R | t], double) or, if that is null, cloud_tf0.
+  const float* cloud;
+  const int* cloud_offsets;
+  const double* cloud_tf;
+  double cloud_tf0[12];
+  float sqr_min_dist, sqr_max_dist, z_min, z_max;
+  float* out_origo;         // B x 2 (may be null): dataContainer origo = laser position * scaleToMap
   float neg_zero;           // -0.0f, deliberately opaque to the compiler (see mul2_exact in match_kernel.cuh)
+  int pace_slack;           // > 0: groups of a CTA keep within this many evaluations of the slowest one (see match_kernel)
   int prefetch;             // != 0: L2 bulk prefetch of the part of a scan that is read from global memory
   // diagnostics (hsb_set_tuning "trace"): per scan 8 x u64 = {start, after coarsest level, ..., end (slot 1+levels), -, smid (slot 7)}
   unsigned long long* trace;

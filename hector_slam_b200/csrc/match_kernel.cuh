@@ -433,6 +433,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
   return v;
 }
+__device__ __forceinline__ unsigned warp_id() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%warpid;" : "=r"(v));
+  return v;
+}
 __device__ __forceinline__ unsigned sm_id() {
   unsigned v;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
@@ -509,22 +514,98 @@ __device__ __forceinline__ int stage_from_ranges(const float* __restrict__ r_sca
   return total;
 }
 
+// ---- N2, default path: sensor_msgs/PointCloud (laser frame) -> DataContainer endpoints, fused the same way ----
+// Restates HectorMappingRos::rosPointCloudToDataContainer (hector_mapping/src/HectorMappingRos.cpp:509-542), the
+// converter a default node uses (use_tf_scan_transformation = true, :82, called at :283): per Point32 (x, y, z):
+//   dist_sqr = x*x + y*y in float (:524); keep sqr_min < dist_sqr < sqr_max (:526); drop x < 0 && dist_sqr < 0.5 (:528);
+//   p = laserTransform * (x, y, z) in DOUBLE — tf::Transform::operator* = row.dot(v) + origin, dot = r0*x + r1*y + r2*z
+//   (tf/LinearMath) (:532); z_laser = float(p.z - laserPos.z) must lie in (z_min, z_max) (:534-536);
+//   endpoint = Vector2f(p.x, p.y) * scaleToMap: double -> float, then one float product (:538).
+// Every operation is rounded separately (__dmul_rn / __dadd_rn), like the node's x86-64 build.  Kept endpoints are
+// compacted in input order.  Warp w converts the contiguous range [w*chunk, (w+1)*chunk) of the cloud.
+struct CloudPoint {
+  float ex, ey;
+  bool keep;
+};
+__device__ __forceinline__ CloudPoint cloud_point(const float* __restrict__ xyz, int i, const double* T, float min2, float max2,
+                                                  float zmin, float zmax, float scale) {
+  const float x = __ldg(xyz + 3 * (size_t)i), y = __ldg(xyz + 3 * (size_t)i + 1), z = __ldg(xyz + 3 * (size_t)i + 2);
+  const float d2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+  CloudPoint o;
+  o.keep = (d2 > min2) && (d2 < max2) && !((x < 0.0f) && (d2 < 0.50f));
+  const double vx = (double)x, vy = (double)y, vz = (double)z;
+  const double bx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], vx), __dmul_rn(T[1], vy)), __dmul_rn(T[2], vz)), T[3]);
+  const double by = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], vx), __dmul_rn(T[5], vy)), __dmul_rn(T[6], vz)), T[7]);
+  const double bz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], vx), __dmul_rn(T[9], vy)), __dmul_rn(T[10], vz)), T[11]);
+  const float zl = (float)__dsub_rn(bz, T[11]);
+  o.keep = o.keep && (zl > zmin) && (zl < zmax);
+  o.ex = __fmul_rn((float)bx, scale);
+  o.ey = __fmul_rn((float)by, scale);
+  return o;
+}
+template <int W>
+__device__ __forceinline__ int stage_from_cloud(const float* __restrict__ xyz, int n_in, const double* T, float min2, float max2,
+                                                float zmin, float zmax, float scale, float2* dst, int* warp_cnt, int g, int w,
+                                                int lane) {
+  const int chunk = (n_in + W - 1) / W;
+  const int b0 = w * chunk, b1 = min(n_in, b0 + chunk);
+  int mine = 0;
+  if (W > 1) {
+    for (int base = b0; base < b1; base += 32) {
+      const int i = base + lane;
+      const bool v = (i < b1) && cloud_point(xyz, i, T, min2, max2, zmin, zmax, scale).keep;
+      mine += __popc(__ballot_sync(0xffffffffu, v));
+    }
+    if (lane == 0) warp_cnt[w] = mine;
+    group_sync<W>(g);
+  }
+  int off = 0, total = 0;
+  if (W > 1) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const int c = warp_cnt[k];
+      if (k < w) off += c;
+      total += c;
+    }
+  }
+  for (int base = b0; base < b1; base += 32) {
+    const int i = base + lane;
+    CloudPoint p;
+    p.keep = false;
+    if (i < b1) p = cloud_point(xyz, i, T, min2, max2, zmin, zmax, scale);
+    const unsigned m = __ballot_sync(0xffffffffu, p.keep);
+    if (p.keep) dst[off + __popc(m & ((1u << lane) - 1u))] = make_float2(p.ex, p.ey);
+    off += __popc(m);
+  }
+  if (W == 1) total = off;
+  group_sync<W>(g);
+  return total;
+}
+
 // Shared-memory carve-up for G groups: [G] mbarriers | [G][2][9][32] reduction slots | points
 template <int W, int G>
 struct MatchSmem {
   static constexpr int kBarBytes = (G * 8 + 15) / 16 * 16;   // mbarriers, padded: the reduction rows are read as float4
   static constexpr int kRedFloats = (W > 1) ? G * 2 * 9 * 32 : 0;
-  static constexpr int kCntInts = G * 32;
-  static constexpr int kHeaderBytes = ((kBarBytes + kRedFloats * 4 + kCntInts * 4) + 15) / 16 * 16;
+  static constexpr int kCntInts = (W > 1) ? G * 32 : 0;      // per-warp counts of the fused conversions (W > 1 only)
+  static constexpr int kProgInts = (G > 1) ? 32 : 0;         // evaluations completed per group (pacing)
+  static constexpr int kHeaderBytes = ((kBarBytes + kRedFloats * 4 + kCntInts * 4 + kProgInts * 4) + 15) / 16 * 16;
+};
+
+// one-warp scans grouped into CTAs: ask for the registers of 28 warps per SM like the G = 1 shape has
+template <int W, int G>
+struct MatchBounds {
+  static constexpr int kMinBlocks = (W == 1 && 28 % G == 0) ? 28 / G : 1;
 };
 
 template <int W, int G, int MODE, int U, bool PACK>
-__global__ void __launch_bounds__(W * G * 32)
+__global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
     match_kernel(const __grid_constant__ HsbMatchParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* mbars = reinterpret_cast<uint64_t*>(smem_raw);
   float* red_all = reinterpret_cast<float*>(smem_raw + MatchSmem<W, G>::kBarBytes);
   int* cnt_all = reinterpret_cast<int*>(smem_raw + MatchSmem<W, G>::kBarBytes + MatchSmem<W, G>::kRedFloats * 4);
+  volatile int* prog = reinterpret_cast<volatile int*>(cnt_all + MatchSmem<W, G>::kCntInts);
   float2* spts_all = reinterpret_cast<float2*>(smem_raw + MatchSmem<W, G>::kHeaderBytes);
 
   constexpr int GT = W * 32;  // threads per group
@@ -540,13 +621,29 @@ __global__ void __launch_bounds__(W * G * 32)
 
   if (t == 0) mbar_init(mbar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // Pacing (G > 1, P.pace_slack > 0).  Measured with the per-scan timeline (profiles/r02_k1_timeline.md): the warps of
+  // an SM do NOT advance at the same rate — of 28 identical one-warp scans started together the first finishes after
+  // 95 us, the last after 142 us — so a one-wave batch ends with a long, thinly occupied tail.  Groups of one CTA
+  // therefore publish how many evaluations they have completed and a group that is more than `pace_slack` ahead of
+  // the slowest one sleeps: its issue slots and texture bandwidth go to the stragglers and all scans of the CTA end
+  // within ~pace_slack evaluations of each other.  No arithmetic is involved: results are unchanged.
+  const bool pace = (G > 1) && P.pace_slack > 0;
+  int evals_done = 0;
+  if (G > 1) {
+    if (threadIdx.x < 32) prog[threadIdx.x] = 0x7fffffff;   // slots of absent / finished groups never hold anyone back
+  }
   __syncthreads();
+  if (pace && t == 0 && blockIdx.x * G + g < P.B) prog[g] = 0;
+  if (G > 1) __syncthreads();
 
   uint32_t phase = 0;
   int red_flip = 0;
   for (int scan = blockIdx.x * G + g; scan < P.B; scan += gridDim.x * G) {
     int beg, n;
-    if (P.offsets) {
+    if (P.cloud) {
+      beg = P.cloud_offsets[scan];
+      n = P.cloud_offsets[scan + 1] - beg;   // input points; replaced by the number kept below
+    } else if (P.offsets) {
       beg = P.offsets[scan];
       n = P.offsets[scan + 1] - beg;
     } else {
@@ -562,6 +659,16 @@ __global__ void __launch_bounds__(W * G * 32)
       // raw ranges in: convert + compact straight into shared memory (host guarantees cap >= n_beams)
       n = stage_from_ranges<W>(P.ranges + (size_t)scan * P.n_beams, P.beam_cs, P.n_beams, P.range_min, P.range_max_c,
                                P.scale_to_map, spts, warp_cnt, g, w, lane);
+      ns = n;
+      staged = true;
+    } else if (P.cloud) {
+      const double* T = P.cloud_tf ? P.cloud_tf + 12 * (size_t)scan : P.cloud_tf0;
+      n = stage_from_cloud<W>(P.cloud + 3 * (size_t)beg, n, T, P.sqr_min_dist, P.sqr_max_dist, P.z_min, P.z_max,
+                              P.scale_to_map, spts, warp_cnt, g, w, lane);
+      if (P.out_origo && t == 0) {   // dataContainer.setOrigo(Vector2f(laserPos.x(), laserPos.y()) * scaleToMap)  (:516-517)
+        P.out_origo[2 * (size_t)scan] = __fmul_rn((float)T[3], P.scale_to_map);
+        P.out_origo[2 * (size_t)scan + 1] = __fmul_rn((float)T[7], P.scale_to_map);
+      }
       ns = n;
       staged = true;
     } else if (cap > 0 && n > 0 && (n < cap || (!PACK && cap - 2 >= GT))) {
@@ -666,6 +773,16 @@ __global__ void __launch_bounds__(W * G * 32)
             a.h12 = v[5]; a.d0 = v[6];  a.d1 = v[7];  a.d2 = v[8];
             red_flip ^= 1;
           }
+          if (pace) {
+            ++evals_done;
+            if (t == 0) prog[g] = evals_done;
+            for (;;) {
+              const int mine = lane < G ? prog[lane] : 0x7fffffff;
+              const int slowest = __reduce_min_sync(0xffffffffu, mine);
+              if (evals_done <= slowest + P.pace_slack) break;
+              __nanosleep(200);
+            }
+          }
           last = a;
           if (a.h00 != 0.0f && a.h11 != 0.0f) {  // ScanMatcher.h:201
             float d0, d1, d2;
@@ -683,8 +800,13 @@ __global__ void __launch_bounds__(W * G * 32)
         if (P.trace && t == 0) P.trace[8 * (size_t)scan + (P.levels - lvl)] = global_timer_ns();
       }
     }
+    if (pace && n <= 0) {   // nothing evaluated: account for the evaluations the others wait for
+      for (int lvl = 0; lvl < P.levels; ++lvl) evals_done += P.lv[lvl].evals;
+      if (t == 0) prog[g] = evals_done;
+    }
     if (P.trace && t == 0) {
       P.trace[8 * (size_t)scan + 1 + P.levels] = global_timer_ns();
+      P.trace[8 * (size_t)scan + 6] = warp_id();
       P.trace[8 * (size_t)scan + 7] = sm_id();
     }
     if (t == 0) {
@@ -702,6 +824,7 @@ __global__ void __launch_bounds__(W * G * 32)
     }
     if (cap > 0) group_sync<W>(g);  // everyone done with spts before the next bulk copy lands
   }
+  if (pace && t == 0) prog[g] = 0x7fffffff;   // this group is done: nobody waits for it any more
 }
 
 // The conversion alone (one scan, one CTA of 8 warps), for the N2 parity tests.
@@ -714,8 +837,36 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) *out_n = n;
 }
 
-// N3: OccGridMapUtil::getLikelihoodForState (OccGridMapUtil.h:189-221) for a batch of poses, one warp
-// per pose.  interpMapValue (:233-285) is the value-only bilinear interpolation: 0 out of bounds.
+__global__ void __launch_bounds__(256)
+    cloud_to_points_kernel(const float* __restrict__ xyz, int n_in, const double* __restrict__ T, float min2, float max2, float zmin,
+                           float zmax, float scale, float2* __restrict__ out, int* __restrict__ out_n) {
+  __shared__ int warp_cnt[32];
+  const int n = stage_from_cloud<8>(xyz, n_in, T, min2, max2, zmin, zmax, scale, out, warp_cnt, 0, threadIdx.x >> 5,
+                                    threadIdx.x & 31);
+  if (threadIdx.x == 0) *out_n = n;
+}
+
+// N3: OccGridMapUtil::getLikelihoodForState (OccGridMapUtil.h:189-221) for one state (map coordinates of the level),
+// evaluated by one warp; every lane returns the value.  interpMapValue (:233-285) is the value-only bilinear
+// interpolation: 0 out of bounds, so such an endpoint contributes funval = 1.
+template <int MODE>
+__device__ __forceinline__ float warp_likelihood(const LevelRegs& LR, float pt_scale, const float2* __restrict__ pts, int n, float ex,
+                                                 float ey, float psi, int lane) {
+  const float cs = cosf_glibc(psi) * pt_scale, ss = sinf_glibc(psi) * pt_scale;
+  float residual = 0.0f;
+  for (int i = lane; i < n; i += 32) {
+    const float2 p = pts[i];
+    PointPre pre;
+    point_address<MODE>(LR, p.x, p.y, true, cs, ss, ex, ey, pre);
+    const float4 v = point_fetch<MODE>(LR, pre);
+    const float xi = 1.0f - pre.fx, yi = 1.0f - pre.fy;
+    const float m = (v.x * xi + v.y * pre.fx) * yi + (v.z * xi + v.w * pre.fx) * pre.fy;  // :282-284
+    residual += pre.inside ? (1.0f - m) : 1.0f;                                         // :216-217
+  }
+  residual = warp_sum(residual);
+  return 1.0f - residual / (float)n;  // getLikelihoodForResidual :203-209
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128)
     likelihood_kernel(const HsbLevelDev L, int B, const float* __restrict__ poses_world, const float2* __restrict__ pts_all,
@@ -730,23 +881,80 @@ __global__ void __launch_bounds__(128)
       beg = offsets[b];
       n = offsets[b + 1] - beg;
     }
-    const float2* pts = pts_all + beg;
     float ex, ey;
     affine_apply_exact(L.mtw, poses_world[3 * b], poses_world[3 * b + 1], ex, ey);
-    const float psi = poses_world[3 * b + 2];
-    const float cs = cosf_glibc(psi) * L.pt_scale, ss = sinf_glibc(psi) * L.pt_scale;
-    float residual = 0.0f;
-    for (int i = lane; i < n; i += 32) {
-      const float2 p = pts[i];
-      PointPre pre;
-      point_address<MODE>(LR, p.x, p.y, true, cs, ss, ex, ey, pre);
-      const float4 v = point_fetch<MODE>(LR, pre);
-      const float xi = 1.0f - pre.fx, yi = 1.0f - pre.fy;
-      const float m = (v.x * xi + v.y * pre.fx) * yi + (v.z * xi + v.w * pre.fx) * pre.fy;  // :282-284
-      residual += pre.inside ? (1.0f - m) : 1.0f;                                         // :216-217
+    const float lh = warp_likelihood<MODE>(LR, L.pt_scale, pts_all + beg, n, ex, ey, poses_world[3 * b + 2], lane);
+    if (lane == 0) out[b] = lh;
+  }
+}
+
+// N3: OccGridMapUtil::getCovarianceForPose (OccGridMapUtil.h:106-160) + getCovMatrixWorldCoords (:162-187) for a batch of
+// poses: one CTA of 7 warps per pose, warp k evaluates the likelihood of sigma point k (:119-135: +-1.5 cells in x and
+// y, +-0.05 rad, the pose itself), thread 0 forms the likelihood-weighted mean and covariance with the fixed-size
+// Eigen operations in the order oracle/shim fixes: likelihoods.sum() by recursive halving, mean += point * lh,
+// mean *= 1/sum, cov += (lh * inv) * (d * d^T), every operation rounded separately.
+template <int MODE>
+__global__ void __launch_bounds__(224)
+    covariance_kernel(const HsbLevelDev L, int B, const float* __restrict__ poses_world, const float2* __restrict__ pts_all,
+                      const int* __restrict__ offsets, int n_shared, float cell_length, float* __restrict__ out_map,
+                      float* __restrict__ out_world) {
+  __shared__ float lhs[7];
+  const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+  const LevelRegs LR = level_regs(L);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    int beg = 0, n = n_shared;
+    if (offsets) {
+      beg = offsets[b];
+      n = offsets[b + 1] - beg;
     }
-    residual = warp_sum(residual);
-    if (lane == 0) out[b] = 1.0f - residual / (float)n;  // getLikelihoodForResidual :203-209
+    float x, y;
+    affine_apply_exact(L.mtw, poses_world[3 * b], poses_world[3 * b + 1], x, y);   // getMapCoordsPose
+    const float ang = poses_world[3 * b + 2];
+    const float dt = 1.5f, da = 0.05f;                                             // :109-111
+    float sx = x, sy = y, sa = ang;
+    if (k == 0) sx = __fadd_rn(x, dt);
+    else if (k == 1) sx = __fsub_rn(x, dt);
+    else if (k == 2) sy = __fadd_rn(y, dt);
+    else if (k == 3) sy = __fsub_rn(y, dt);
+    else if (k == 4) sa = __fadd_rn(ang, da);
+    else if (k == 5) sa = __fsub_rn(ang, da);
+    const float lh = warp_likelihood<MODE>(LR, L.pt_scale, pts_all + beg, n, sx, sy, sa, lane);
+    if (lane == 0) lhs[k] = lh;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float sp[7][3] = {{__fadd_rn(x, dt), y, ang}, {__fsub_rn(x, dt), y, ang}, {x, __fadd_rn(y, dt), ang},
+                              {x, __fsub_rn(y, dt), ang}, {x, y, __fadd_rn(ang, da)}, {x, y, __fsub_rn(ang, da)}, {x, y, ang}};
+      const float sum = __fadd_rn(__fadd_rn(lhs[0], __fadd_rn(lhs[1], lhs[2])),
+                                  __fadd_rn(__fadd_rn(lhs[3], lhs[4]), __fadd_rn(lhs[5], lhs[6])));
+      const float inv = __fdiv_rn(1.0f, sum);                                       // :137
+      float mean[3] = {0.f, 0.f, 0.f};
+      for (int i = 0; i < 7; ++i)
+        for (int c = 0; c < 3; ++c) mean[c] = __fadd_rn(mean[c], __fmul_rn(sp[i][c], lhs[i]));   // :144
+      for (int c = 0; c < 3; ++c) mean[c] = __fmul_rn(mean[c], inv);                             // :147
+      float cov[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < 7; ++i) {                                                               // :151-154
+        const float d[3] = {__fsub_rn(sp[i][0], mean[0]), __fsub_rn(sp[i][1], mean[1]), __fsub_rn(sp[i][2], mean[2])};
+        const float wgt = __fmul_rn(lhs[i], inv);
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) cov[3 * r + c] = __fadd_rn(cov[3 * r + c], __fmul_rn(wgt, __fmul_rn(d[r], d[c])));
+      }
+      if (out_map)
+        for (int c = 0; c < 9; ++c) out_map[9 * (size_t)b + c] = cov[c];
+      if (out_world) {                                                                            // :162-187
+        float* w = out_world + 9 * (size_t)b;
+        const float st = cell_length, st2 = __fmul_rn(st, st);
+        w[0] = __fmul_rn(cov[0], st2);
+        w[4] = __fmul_rn(cov[4], st2);
+        w[3] = __fmul_rn(cov[3], st2);
+        w[1] = w[3];
+        w[6] = __fmul_rn(cov[6], st);
+        w[2] = w[6];
+        w[7] = __fmul_rn(cov[7], st);
+        w[5] = w[7];
+        w[8] = cov[8];
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -74,8 +74,47 @@ __global__ void occupancy_kernel(const float* __restrict__ logodds, int8_t* __re
   }
 }
 
-// N4: DistanceMeasurementProvider::checkOccupancyBresenhami (HectorMapTools.h:133-216), one warp per ray.
-// Same closed-form line as K2; 32 cells are tested per step and the first occupied one wins.
+// N4: DistanceMeasurementProvider::checkOccupancyBresenhami (HectorMapTools.h:148-214, bresenham2D :216-237), one warp
+// per ray.  Same closed-form line as K2; 32 cells are tested per step and the first occupied one wins.
+__device__ __forceinline__ float warp_raycast(const float* __restrict__ logodds, int sx, int sy, int2 p0, int2 p1, int lane,
+                                              int2& hit) {
+  float dist = -1.0f;
+  hit = make_int2(-1, -1);
+  const bool ok = p0.x >= 0 && p0.x < sx && p0.y >= 0 && p0.y < sy && p1.x >= 0 && p1.x < sx && p1.y >= 0 && p1.y < sy;  // :155-166
+  if (ok) {
+    const int dx = p1.x - p0.x, dy = p1.y - p0.y;
+    const unsigned adx = (unsigned)abs(dx), ady = (unsigned)abs(dy);
+    const int off_dx = dx > 0 ? 1 : -1, off_dy = (dy > 0 ? 1 : -1) * sx;   // :174-175
+    unsigned ada, adb;
+    int off_a, off_b;
+    if (adx >= ady) { ada = adx; adb = ady; off_a = off_dx; off_b = off_dy; }   // :182-189
+    else            { ada = ady; adb = adx; off_a = off_dy; off_b = off_dx; }
+    const unsigned err0 = ada / 2u;
+    const unsigned start = (unsigned)p0.y * (unsigned)sx + (unsigned)p0.x;
+    const unsigned steps = min(5000u, ada);                                    // :218
+    for (unsigned base = 0; base < steps; base += 32u) {
+      const unsigned i = base + (unsigned)lane;
+      unsigned off = 0;
+      bool occ = false;
+      if (i < steps) {
+        const unsigned carries = (unsigned)(((unsigned long long)err0 + (unsigned long long)i * adb) / ada);
+        off = start + (unsigned)((int)i * off_a) + (unsigned)((int)carries * off_b);
+        occ = logodds[off] > 0.0f;                                             // data[offset] == 100  (:223)
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, occ);
+      if (m) {
+        const int first = __ffs(m) - 1;
+        const unsigned hoff = __shfl_sync(0xffffffffu, off, first);
+        hit = make_int2((int)(hoff % (unsigned)sx), (int)(hoff / (unsigned)sx));   // :194
+        const float fx = (float)(p0.x - hit.x), fy = (float)(p0.y - hit.y);
+        dist = (float)(int)__fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));  // int distMap = norm  (:196)
+        break;
+      }
+    }
+  }
+  return dist;
+}
+
 __global__ void __launch_bounds__(256)
     raycast_kernel(const float* __restrict__ logodds, int sx, int sy, int B, const int2* __restrict__ begin,
                    const int2* __restrict__ end, float* __restrict__ out_dist, int2* __restrict__ out_hit) {
@@ -83,44 +122,44 @@ __global__ void __launch_bounds__(256)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int b = warp; b < B; b += nwarps) {
-    const int2 p0 = begin[b], p1 = end[b];
-    float dist = -1.0f;
-    int2 hit = make_int2(-1, -1);
-    const bool ok = p0.x >= 0 && p0.x < sx && p0.y >= 0 && p0.y < sy && p1.x >= 0 && p1.x < sx && p1.y >= 0 && p1.y < sy;  // :141-154
-    if (ok) {
-      const int dx = p1.x - p0.x, dy = p1.y - p0.y;
-      const unsigned adx = (unsigned)abs(dx), ady = (unsigned)abs(dy);
-      const int off_dx = dx > 0 ? 1 : -1, off_dy = (dy > 0 ? 1 : -1) * sx;   // :162-163
-      unsigned ada, adb;
-      int off_a, off_b;
-      if (adx >= ady) { ada = adx; adb = ady; off_a = off_dx; off_b = off_dy; }   // :170-177
-      else            { ada = ady; adb = adx; off_a = off_dy; off_b = off_dx; }
-      const unsigned err0 = ada / 2u;
-      const unsigned start = (unsigned)p0.y * (unsigned)sx + (unsigned)p0.x;
-      const unsigned steps = min(5000u, ada);                                    // :203
-      for (unsigned base = 0; base < steps; base += 32u) {
-        const unsigned i = base + (unsigned)lane;
-        unsigned off = 0;
-        bool occ = false;
-        if (i < steps) {
-          const unsigned carries = (unsigned)(((unsigned long long)err0 + (unsigned long long)i * adb) / ada);
-          off = start + (unsigned)((int)i * off_a) + (unsigned)((int)carries * off_b);
-          occ = logodds[off] > 0.0f;                                             // data[offset] == 100  (:208)
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, occ);
-        if (m) {
-          const int first = __ffs(m) - 1;
-          const unsigned hoff = __shfl_sync(0xffffffffu, off, first);
-          hit = make_int2((int)(hoff % (unsigned)sx), (int)(hoff / (unsigned)sx));   // :182
-          const float fx = (float)(p0.x - hit.x), fy = (float)(p0.y - hit.y);
-          dist = (float)(int)__fsqrt_rn(__fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy)));  // int distMap = norm  (:184)
-          break;
-        }
-      }
-    }
+    int2 hit;
+    const float dist = warp_raycast(logodds, sx, sy, begin[b], end[b], lane, hit);
     if (lane == 0) {
       out_dist[b] = dist;
       if (out_hit) out_hit[b] = hit;
+    }
+  }
+}
+
+// N4: DistanceMeasurementProvider::getDist (HectorMapTools.h:133-147) for B world-frame rays: world -> cell with
+// CoordinateTransformer<float>::getC2Coords ((w - origo) * inv_scale, :93-96) truncated by cast<int> (:136-137; a
+// non-finite or absurd coordinate is treated as outside the map), the ray cast, the hit cell back to the world with
+// getC1Coords (origo + cell * scale, :88-91) and the distance scaled by getC1Scale (scale * dist, :98-101; nothing hit:
+// scale * -1 as in the reference, hit_world = (0, 0) and found = 0 where the reference leaves hitCoords undefined).
+__global__ void __launch_bounds__(256)
+    getdist_kernel(const float* __restrict__ logodds, int sx, int sy, int B, float origo_x, float origo_y, float scale,
+                   float inv_scale, const float2* __restrict__ begin_world, const float2* __restrict__ end_world,
+                   float* __restrict__ out_dist, float2* __restrict__ out_hit_world, int* __restrict__ out_found) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b < B; b += nwarps) {
+    const float2 bw = begin_world[b], ew = end_world[b];
+    const float bx = __fmul_rn(__fsub_rn(bw.x, origo_x), inv_scale), by = __fmul_rn(__fsub_rn(bw.y, origo_y), inv_scale);
+    const float ex = __fmul_rn(__fsub_rn(ew.x, origo_x), inv_scale), ey = __fmul_rn(__fsub_rn(ew.y, origo_y), inv_scale);
+    const bool sane = fabsf(bx) < 1.0e9f && fabsf(by) < 1.0e9f && fabsf(ex) < 1.0e9f && fabsf(ey) < 1.0e9f;
+    const int2 p0 = sane ? make_int2((int)bx, (int)by) : make_int2(-1, -1);
+    const int2 p1 = sane ? make_int2((int)ex, (int)ey) : make_int2(-1, -1);
+    int2 hit;
+    const float dist = warp_raycast(logodds, sx, sy, p0, p1, lane, hit);
+    if (lane == 0) {
+      out_dist[b] = __fmul_rn(scale, dist);
+      const bool found = dist >= 0.0f;
+      if (out_found) out_found[b] = found ? 1 : 0;
+      if (out_hit_world)
+        out_hit_world[b] = found ? make_float2(__fadd_rn(origo_x, __fmul_rn((float)hit.x, scale)),
+                                               __fadd_rn(origo_y, __fmul_rn((float)hit.y, scale)))
+                                 : make_float2(0.0f, 0.0f);
     }
   }
 }

@@ -192,6 +192,33 @@ def make_range_batch(world: World, poses: np.ndarray, noise_seed: int = 7, sigma
     return out
 
 
+def ranges_to_cloud(ranges: np.ndarray, angles: np.ndarray = _ANGLES, cutoff: float = 30.0) -> np.ndarray:
+    """A sensor_msgs/PointCloud in the LASER frame from one scan's ranges, the way the node obtains its default input
+    (laser_geometry projectLaser(scan, cloud, 30.0), HectorMappingRos.cpp:274): one Point32 (x, y, z = 0) per return
+    with range_min <= r <= min(range_max, cutoff), beam order.  (n, 3) float32 — input generator, not product code."""
+    r = ranges.astype(np.float32)
+    keep = (r >= RANGE_MIN) & (r <= np.float32(min(float(RANGE_MAX), cutoff)))
+    a = angles[keep].astype(np.float32)
+    pts = np.zeros((int(keep.sum()), 3), dtype=np.float32)
+    pts[:, 0] = (np.cos(a).astype(np.float32) * r[keep]).astype(np.float32)
+    pts[:, 1] = (np.sin(a).astype(np.float32) * r[keep]).astype(np.float32)
+    return pts
+
+
+def laser_transform(xyz=(0.12, -0.03, 0.31), rpy=(0.02, -0.035, 0.05)) -> np.ndarray:
+    """tf base_frame <- laser frame as 12 float64, rows of [R | t] (R = Rz(yaw) Ry(pitch) Rx(roll))."""
+    r, p, y = rpy
+    cr, sr, cp, sp, cy, sy = math.cos(r), math.sin(r), math.cos(p), math.sin(p), math.cos(y), math.sin(y)
+    R = np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                  [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                  [-sp, cp * sr, cp * cr]], dtype=np.float64)
+    return np.ascontiguousarray(np.concatenate([R, np.asarray(xyz, np.float64)[:, None]], axis=1).reshape(12))
+
+
+# HectorMappingRos.cpp:98-108 defaults: laser_min_dist 0.4 m, laser_max_dist 30 m (squared, as floats), z window +-1 m
+CLOUD_FORMAT = dict(sqr_laser_min_dist=float(np.float32(0.4 * 0.4)), sqr_laser_max_dist=float(np.float32(30.0 * 30.0)),
+                    laser_z_min_value=-1.0, laser_z_max_value=1.0)
+
 SCAN_FORMAT = dict(n_beams=N_BEAMS, angle_min=float(ANGLE_MIN), angle_increment=float(ANGLE_INC),
                    range_min=float(RANGE_MIN), range_max=float(RANGE_MAX))
 

@@ -156,6 +156,33 @@ int hsb_match_batch_ranges(hsb_handle* h, int B, const float* hints_world, const
 int hsb_match_batch_ranges_device(hsb_handle* h, int B, const float* d_hints_world, const float* d_ranges,
                                   float* d_out_poses_world, float* d_out_cov, void* stream);
 
+/* ---- point clouds in (the node's DEFAULT input path) ---------------------------------------------*/
+/* HectorMappingRos::rosPointCloudToDataContainer (hector_mapping/src/HectorMappingRos.cpp:509-542), which a default
+ * node (use_tf_scan_transformation = true, :82) runs on the cloud laser_geometry projected from the scan (:274-283).
+ * The four parameters are the node's (:98-108: laser_min_dist^2, laser_max_dist^2 as floats, laser_z_min/max_value);
+ * laser_transform is tf's base_frame <- laser frame as 12 doubles, rows of [R | t] (tfScalar is double). */
+typedef struct hsb_cloud_format {
+  double laser_transform[12];
+  float  sqr_laser_min_dist;   /* keep sqr_min < x*x + y*y            (:526) */
+  float  sqr_laser_max_dist;   /*      x*x + y*y < sqr_max                   */
+  float  laser_z_min_value;    /* keep z_min < z(base) - z(laser) < z_max (:534-536) */
+  float  laser_z_max_value;
+} hsb_cloud_format;
+int hsb_set_cloud_format(hsb_handle* h, const hsb_cloud_format* fmt);
+/* The conversion alone for one cloud: points_xyz = n Point32 triples (x, y, z float32, laser frame, exactly
+ * sensor_msgs/PointCloud::points' memory) -> kept endpoints in level-0 cell units, input order (capacity n x 2),
+ * *out_n = number kept, out_origo (may be NULL) = the container's origo (:516-517).  Host buffers. */
+int hsb_cloud_to_points(hsb_handle* h, const float* points_xyz, int n, float* out_points_xy, int* out_n, float out_origo[2]);
+/* hsb_match_batch with that conversion fused into the match kernel's staging step: cloud b is the triples
+ * points_xyz[3*offsets[b] .. 3*offsets[b+1]).  `transforms` (B x 12 doubles, may be NULL) gives every cloud its own
+ * laser transform (a tf lookup per scan stamp, :262); NULL uses the format's.  out_origo (B x 2, may be NULL)
+ * receives each container's origo, which hsb_update_by_scan needs.  Host buffers / device buffers + stream. */
+int hsb_match_batch_cloud(hsb_handle* h, int B, const float* hints_world, const float* points_xyz, const int* offsets,
+                          const double* transforms, float* out_poses_world, float* out_cov, float* out_origo);
+int hsb_match_batch_cloud_device(hsb_handle* h, int B, const float* d_hints_world, const float* d_points_xyz,
+                                 const int* d_offsets, int max_points_per_scan, const double* d_transforms,
+                                 float* d_out_poses_world, float* d_out_cov, float* d_out_origo, void* stream);
+
 /* OccGridMapUtil::getCompleteHessianDerivs — map/OccGridMapUtil.h:64-104, one evaluation on one
  * level: `pose_map` and `points_level_xy` are in that level's cell units.  This is the finest
  * seam: the reference's own ScanMatcher can drive it one evaluation at a time. */
@@ -236,6 +263,16 @@ int hsb_download_occupancy(hsb_handle* h, int level, int8_t* occupancy_host_out)
 int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses_world, const float* points_xy,
                          const int* offsets, int n_shared, float* out_likelihood);
 
+/* OccGridMapUtil::getCovarianceForPose — map/OccGridMapUtil.h:106-160 — the sigma-point covariance of a pose: the
+ * likelihoods (above) of the pose and of six neighbours (+-1.5 cells in x / y, +-0.05 rad) weight a mean and a 3x3
+ * covariance in the level's MAP units; out_cov_world additionally applies getCovMatrixWorldCoords (:162-187: cell
+ * length squared on the translation block, cell length on the mixed terms).  Poses are world poses (converted with
+ * getMapCoordsPose of `level`); scans as in hsb_likelihood_batch.  Either output may be NULL.  Row-major 3x3 each.
+ * (Dead code in the reference's own node, but part of the library interface; the reference prints the seven
+ * likelihoods to stdout at :139 — not reproduced.)  Host buffers. */
+int hsb_covariance_batch(hsb_handle* h, int level, int B, const float* poses_world, const float* points_xy,
+                         const int* offsets, int n_shared, float* out_cov_map, float* out_cov_world);
+
 /* hector_map_tools' DistanceMeasurementProvider::checkOccupancyBresenhami
  * (hector_map_tools/include/hector_map_tools/HectorMapTools.h:133-216, bresenham2D :200-216), B rays
  * at once on one level: walk the Bresenham line from begin cell to end cell (start included, end
@@ -245,6 +282,18 @@ int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses_wor
  * cell (x, y) or (-1, -1).  begin_cells / end_cells: B x 2 int32 (x, y).  Host buffers. */
 int hsb_raycast_batch(hsb_handle* h, int level, int B, const int* begin_cells, const int* end_cells, float* out_dist,
                       int* out_hit);
+
+/* The origin a nav_msgs/OccupancyGrid of `level` carries (HectorMappingRos::setServiceGetMapData,
+ * hector_mapping/src/HectorMappingRos.cpp:546-550): world coordinates of cell (0,0) minus half a cell. */
+int hsb_get_map_origin(const hsb_handle* h, int level, float out[2]);
+/* DistanceMeasurementProvider::getDist (HectorMapTools.h:133-147), B world-frame rays at once: both end points go
+ * through CoordinateTransformer<float>::getC2Coords ((w - origin) * (1.0f / resolution), truncated to int), the ray is
+ * cast as in hsb_raycast_batch, out_dist[b] = resolution * cells (or resolution * -1 if nothing was hit, as the
+ * reference returns), out_hit_world (B x 2, may be NULL) = origin + hit cell * resolution, out_found (may be NULL) =
+ * 1 where something was hit (the reference leaves the hit undefined otherwise; (0, 0) here).  This is what
+ * hector_map_server's get_distance_to_obstacle service calls (hector_map_server.cpp:123).  Host buffers. */
+int hsb_get_dist_batch(hsb_handle* h, int level, int B, const float* begin_world, const float* end_world, float* out_dist,
+                       float* out_hit_world, int* out_found);
 
 /* ---- diagnostics ----------------------------------------------------------------------------*/
 const char* hsb_last_error(const hsb_handle* h);

@@ -679,6 +679,48 @@ float hso_likelihood(void* hv, int level, const float pose_map[3], const float* 
   return 1 - (residual / sizef);
 }
 
+/* OccGridMapUtil::getCovarianceForPose — map/OccGridMapUtil.h:106-160 — and getCovMatrixWorldCoords — :162-187.
+ * Seven sigma points (+-1.5 cells, +-0.05 rad, the pose itself), their likelihoods, the likelihood-weighted mean and
+ * the weighted sum of outer products.  Fixed-size Eigen operations in the shim's order: likelihoods.sum() of 7 by
+ * recursive halving = (l0 + (l1 + l2)) + ((l3 + l4) + (l5 + l6)); vector * scalar and matrix += element-wise. */
+void hso_covariance_for_pose(void* hv, int level, const float pose_map[3], const float* pts_level, int n, float out_map[9],
+                             float out_world[9]) {
+  hso_t* h = (hso_t*)hv;
+  const float dtx = 1.5f, dty = 1.5f, dang = 0.05f; /* :109-111 */
+  const float x = pose_map[0], y = pose_map[1], ang = pose_map[2];
+  float sp[7][3] = {{x + dtx, y, ang}, {x - dtx, y, ang}, {x, y + dty, ang}, {x, y - dty, ang},
+                    {x, y, ang + dang}, {x, y, ang - dang}, {x, y, ang}}; /* :119-125 */
+  float lh[7];
+  for (int i = 0; i < 7; ++i) lh[i] = hso_likelihood(hv, level, sp[i], pts_level, n); /* :129-135 */
+  float sum = (lh[0] + (lh[1] + lh[2])) + ((lh[3] + lh[4]) + (lh[5] + lh[6]));
+  float inv = 1 / sum; /* :137 */
+  float mean[3] = {0.0f, 0.0f, 0.0f};
+  for (int i = 0; i < 7; ++i)
+    for (int k = 0; k < 3; ++k) mean[k] += sp[i][k] * lh[i]; /* :144 */
+  for (int k = 0; k < 3; ++k) mean[k] *= inv;                 /* :147 */
+  float cov[9] = {0};
+  for (int i = 0; i < 7; ++i) { /* :151-154 */
+    float d[3] = {sp[i][0] - mean[0], sp[i][1] - mean[1], sp[i][2] - mean[2]};
+    float wgt = lh[i] * inv;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        float outer = d[r] * d[c];
+        cov[3 * r + c] += wgt * outer;
+      }
+  }
+  memcpy(out_map, cov, sizeof(cov));
+  float st = h->lv[level].cell_length, st2 = st * st; /* :169-170 util::sqr */
+  out_world[0] = cov[0] * st2;                        /* :172 */
+  out_world[4] = cov[4] * st2;
+  out_world[3] = cov[3] * st2;                        /* (1,0) :175 */
+  out_world[1] = out_world[3];
+  out_world[6] = cov[6] * st;                         /* (2,0) :178 */
+  out_world[2] = out_world[6];
+  out_world[7] = cov[7] * st;                         /* (2,1) :181 */
+  out_world[5] = out_world[7];
+  out_world[8] = cov[8];                              /* :184 */
+}
+
 /* hector_map_tools DistanceMeasurementProvider::checkOccupancyBresenhami + bresenham2D
  * (/root/reference/hector_map_tools/include/hector_map_tools/HectorMapTools.h:133-216), on a level's
  * log-odds plane: a cell's nav_msgs value is 100 iff its log-odds is > 0 (HectorMappingRos.cpp:462-465).
@@ -726,6 +768,39 @@ float hso_raycast(void* hv, int level, int x0, int y0, int x1, int y1, int hit[2
   return -1.0f;
 }
 
+/* The nav_msgs/OccupancyGrid origin of a level as HectorMappingRos::setServiceGetMapData derives it
+ * (hector_mapping/src/HectorMappingRos.cpp:546-550): getWorldCoords(0, 0) - cellLength * 0.5 in float. */
+void hso_map_origin(void* hv, int level, float out[2]) {
+  level_t* L = &((hso_t*)hv)->lv[level];
+  float wx, wy;
+  affine2_apply(&L->world_T_map, 0.0f, 0.0f, &wx, &wy);
+  float half = L->cell_length * 0.5f;
+  out[0] = wx - half;
+  out[1] = wy - half;
+}
+
+/* DistanceMeasurementProvider::getDist — hector_map_tools/HectorMapTools.h:133-147 with CoordinateTransformer<float>
+ * (:41-116): getC2Coords = (world - origo) * inv_scale then cast<int> (truncation, :136-137), the ray cast above,
+ * getC1Coords = origo + cells * scale for the hit (:141), getC1Scale = scale * dist (:144).  inv_scale = 1.0f /
+ * resolution (:64).  *found = 0 when nothing was hit (the value returned is then scale * -1). */
+float hso_get_dist(void* hv, int level, const float begin_world[2], const float end_world[2], float hit_world[2], int* found) {
+  level_t* L = &((hso_t*)hv)->lv[level];
+  float origo[2];
+  hso_map_origin(hv, level, origo);
+  float scale = L->cell_length, inv_scale = 1.0f / L->cell_length;
+  int bx = (int)((begin_world[0] - origo[0]) * inv_scale), by = (int)((begin_world[1] - origo[1]) * inv_scale);
+  int ex = (int)((end_world[0] - origo[0]) * inv_scale), ey = (int)((end_world[1] - origo[1]) * inv_scale);
+  int hit[2];
+  float dist = hso_raycast(hv, level, bx, by, ex, ey, hit);
+  *found = dist >= 0.0f;
+  hit_world[0] = hit_world[1] = 0.0f;
+  if (*found) {
+    hit_world[0] = origo[0] + (float)hit[0] * scale;
+    hit_world[1] = origo[1] + (float)hit[1] * scale;
+  }
+  return scale * dist;
+}
+
 /* HectorMappingRos::rosLaserScanToDataContainer — hector_mapping/src/HectorMappingRos.cpp:483-507.
  * (That file needs ROS and cannot be compiled here, so this row of the path is pinned by this
  * restatement only.)  `cos(angle)` / `sin(angle)` are called on a float with the <cmath> overloads
@@ -746,6 +821,40 @@ int hso_scan_to_points(const float* ranges, int n_beams, float angle_min, float 
     angle += angle_increment; /* :505 */
   }
   return n;
+}
+
+/* HectorMappingRos::rosPointCloudToDataContainer — hector_mapping/src/HectorMappingRos.cpp:509-542: the node's
+ * DEFAULT input path (use_tf_scan_transformation = true, :82; called at :283).  Point32 fields are float, tf is
+ * double (tfScalar): `laserTransform * tf::Vector3(x, y, z)` is row.dot(v) + origin per row with
+ * dot = r0*x + r1*y + r2*z (tf/LinearMath/Transform.h, Vector3.h), narrowed to float by Eigen::Vector2f(double,
+ * double) (:538) and by the `float pointPosLaserFrameZ` declaration (:534).  transform: 12 doubles, rows of [R | t].
+ * out_xy has room for n x 2; returns the number of endpoints kept, origo (:516-517) in out_origo. */
+int hso_cloud_to_points(const float* xyz, int n, const double* T, float sqr_min_dist, float sqr_max_dist, float z_min,
+                        float z_max, float scale_to_map, float* out_xy, float* out_origo) {
+  const double lx = T[3], ly = T[7], lz = T[11]; /* laserPos = getOrigin()  :515 */
+  if (out_origo) {                               /* :517 Vector2f(laserPos.x(), laserPos.y()) * scaleToMap */
+    out_origo[0] = (float)lx * scale_to_map;
+    out_origo[1] = (float)ly * scale_to_map;
+  }
+  int kept = 0;
+  for (int i = 0; i < n; ++i) {
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    float dist_sqr = x * x + y * y;                                   /* :524 */
+    if ((dist_sqr > sqr_min_dist) && (dist_sqr < sqr_max_dist)) {     /* :526 */
+      if ((x < 0.0f) && (dist_sqr < 0.50f)) continue;                 /* :528-530 */
+      const double vx = (double)x, vy = (double)y, vz = (double)z;
+      const double bx = (T[0] * vx + T[1] * vy + T[2] * vz) + lx;     /* :532 */
+      const double by = (T[4] * vx + T[5] * vy + T[6] * vz) + ly;
+      const double bz = (T[8] * vx + T[9] * vy + T[10] * vz) + lz;
+      float z_laser = (float)(bz - lz);                               /* :534 */
+      if (z_laser > z_min && z_laser < z_max) {                       /* :536 */
+        out_xy[2 * kept] = (float)bx * scale_to_map;                  /* :538 */
+        out_xy[2 * kept + 1] = (float)by * scale_to_map;
+        ++kept;
+      }
+    }
+  }
+  return kept;
 }
 
 /* ---- batch of independent matches (timing harness; same contract as hsref_match_batch) ------ */

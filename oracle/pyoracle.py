@@ -91,6 +91,7 @@ class Oracle:
         sig("update_level", None, vp, i, _f32p, i, _f32p, _f32p)
         sig("match_batch", C.c_double, vp, i, _f32p, _f32p, _i32p, _f32p, _f32p, i)
         sig("likelihood", f, vp, i, _f32p, _f32p, i)
+        sig("covariance_for_pose", None, vp, i, _f32p, _f32p, i, _f32p, _f32p)
 
     def close(self):
         if getattr(self, "h", None):
@@ -194,10 +195,35 @@ class Oracle:
         d = fn(self.h, level, int(begin[0]), int(begin[1]), int(end[0]), int(end[1]), hit)
         return float(d), (int(hit[0]), int(hit[1]))
 
+    def map_origin(self, level: int) -> np.ndarray:
+        """nav_msgs/OccupancyGrid origin of the level (setServiceGetMapData; port only)."""
+        fn = self.lib.hso_map_origin
+        fn.restype = None
+        fn.argtypes = [C.c_void_p, C.c_int, _f32p]
+        out = np.zeros(2, np.float32)
+        fn(self.h, level, out)
+        return out
+
+    def get_dist(self, level: int, begin_world, end_world):
+        """DistanceMeasurementProvider::getDist (port only). -> (dist [m], hit_world (2,), found)"""
+        fn = self.lib.hso_get_dist
+        fn.restype = C.c_float
+        fn.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, C.POINTER(C.c_int)]
+        hw, found = np.zeros(2, np.float32), C.c_int(0)
+        d = fn(self.h, level, _f32(begin_world), _f32(end_world), hw, C.byref(found))
+        return float(d), hw, bool(found.value)
+
     def likelihood(self, level: int, pose_map, pts_level) -> float:
         """OccGridMapUtil::getLikelihoodForState (state and points in the level's cell units)."""
         pts = _f32(pts_level).reshape(-1, 2)
         return float(self._fn("likelihood")(self.h, level, _f32(pose_map), pts, pts.shape[0]))
+
+    def covariance_for_pose(self, level: int, pose_map, pts_level):
+        """OccGridMapUtil::getCovarianceForPose + getCovMatrixWorldCoords. -> (cov_map 3x3, cov_world 3x3)"""
+        pts = _f32(pts_level).reshape(-1, 2)
+        cm, cw = np.zeros(9, np.float32), np.zeros(9, np.float32)
+        self._fn("covariance_for_pose")(self.h, level, _f32(pose_map), pts, pts.shape[0], cm, cw)
+        return cm.reshape(3, 3), cw.reshape(3, 3)
 
     def match_level(self, level: int, hint_world, pts_level, max_iterations: int):
         """ScanMatcher::matchData on one level (1 + max_iterations evaluations)."""
@@ -222,15 +248,74 @@ class Oracle:
         return poses, covs.reshape(B, 3, 3), float(secs)
 
 
-def scan_to_points(ranges, angle_min, angle_increment, range_min, range_max, scale_to_map):
-    """rosLaserScanToDataContainer (HectorMappingRos.cpp:483-507) by the C port. -> (n, 2) float32"""
-    lib = C.CDLL(PORT_LIB)
-    lib.hso_scan_to_points.restype = C.c_int
-    lib.hso_scan_to_points.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _f32p]
+class RefMapTools:
+    """hector_map_tools' DistanceMeasurementProvider compiled from the UNMODIFIED HectorMapTools.h
+    (oracle/maptools_driver.cpp, reference kind only) over an occupancy grid (int8: 0 / 100 / -1)."""
+
+    def __init__(self, occupancy: np.ndarray, resolution: float, origin_xy):
+        self.lib = C.CDLL(REF_LIB)
+        L = self.lib
+        L.hsref_maptools_create.restype = C.c_void_p
+        L.hsref_maptools_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_void_p]
+        L.hsref_maptools_destroy.argtypes = [C.c_void_p]
+        L.hsref_maptools_raycast.restype = C.c_float
+        L.hsref_maptools_raycast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.hsref_maptools_get_dist.restype = C.c_float
+        L.hsref_maptools_get_dist.argtypes = [C.c_void_p, _f32p, _f32p, _f32p, C.POINTER(C.c_int)]
+        occ = np.ascontiguousarray(occupancy, dtype=np.int8)
+        self.h = L.hsref_maptools_create(occ.shape[1], occ.shape[0], resolution, float(origin_xy[0]), float(origin_xy[1]),
+                                         occ.ctypes.data)
+
+    def raycast(self, begin, end):
+        hit = (C.c_int * 2)()
+        d = self.lib.hsref_maptools_raycast(self.h, int(begin[0]), int(begin[1]), int(end[0]), int(end[1]), hit)
+        return float(d), (int(hit[0]), int(hit[1]))
+
+    def get_dist(self, begin_world, end_world):
+        hw, found = np.zeros(2, np.float32), C.c_int(0)
+        d = self.lib.hsref_maptools_get_dist(self.h, _f32(begin_world), _f32(end_world), hw, C.byref(found))
+        return float(d), hw, bool(found.value)
+
+    def close(self):
+        if self.h:
+            self.lib.hsref_maptools_destroy(self.h)
+            self.h = None
+
+
+def _conv_lib(kind: str):
+    if kind == "reference":
+        return C.CDLL(REF_LIB), "hsref_"
+    return C.CDLL(PORT_LIB), "hso_"
+
+
+def scan_to_points(ranges, angle_min, angle_increment, range_min, range_max, scale_to_map, kind: str = "port"):
+    """rosLaserScanToDataContainer (HectorMappingRos.cpp:483-507): the C port, or (kind="reference") the node's own
+    source text compiled by oracle/ros_conv_driver.cpp. -> (n, 2) float32"""
+    lib, p = _conv_lib(kind)
+    fn = getattr(lib, p + "scan_to_points")
+    fn.restype = C.c_int
+    fn.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _f32p]
     r = _f32(ranges).reshape(-1)
     out = np.zeros(2 * r.size, np.float32)
-    n = lib.hso_scan_to_points(r, r.size, angle_min, angle_increment, range_min, range_max, scale_to_map, out)
+    n = fn(r, r.size, angle_min, angle_increment, range_min, range_max, scale_to_map, out)
     return out[: 2 * n].reshape(n, 2).copy()
+
+
+def cloud_to_points(xyz, transform, sqr_min_dist, sqr_max_dist, z_min, z_max, scale_to_map, kind: str = "port"):
+    """rosPointCloudToDataContainer (HectorMappingRos.cpp:509-542). xyz: (n, 3) float32 points in the laser frame
+    (sensor_msgs/PointCloud.points), transform: 12 float64, rows of [R | t] base <- laser.
+    -> (endpoints (k, 2) float32 in map cells, origo (2,) float32)"""
+    lib, p = _conv_lib(kind)
+    fn = getattr(lib, p + "cloud_to_points")
+    fn.restype = C.c_int
+    fn.argtypes = [_f32p, C.c_int, np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS"), C.c_float, C.c_float,
+                   C.c_float, C.c_float, C.c_float, _f32p, _f32p]
+    pts = _f32(xyz).reshape(-1, 3)
+    T = np.ascontiguousarray(transform, dtype=np.float64).reshape(12)
+    out = np.zeros(2 * max(1, pts.shape[0]), np.float32)
+    origo = np.zeros(2, np.float32)
+    n = fn(pts.reshape(-1), pts.shape[0], T, sqr_min_dist, sqr_max_dist, z_min, z_max, scale_to_map, out, origo)
+    return out[: 2 * n].reshape(n, 2).copy(), origo
 
 
 def build_map_by_slam(orc: Oracle, world, scale_to_map: float = 20.0, noise_seed: int = 11, sigma: float = 0.01):

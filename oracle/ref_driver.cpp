@@ -15,6 +15,7 @@
 //   hsref_match_level       -> ScanMatcher::matchData               matcher/ScanMatcher.h:54
 //   hsref_update_level      -> OccGridMapBase::updateByScan         map/OccGridMapBase.h:121
 //   hsref_get_prob          -> OccGridMapBase::getGridProbabilityMap map/OccGridMapBase.h:74
+//   hsref_covariance_for_pose -> OccGridMapUtil::getCovarianceForPose / getCovMatrixWorldCoords  map/OccGridMapUtil.h:106-187
 #include <iostream>
 #include <vector>
 #include <climits>
@@ -255,6 +256,26 @@ float hsref_likelihood(void* hv, int level, const float pose_map[3], const float
   hectorslam::DataContainer dc;
   fill(dc, pts_level, n, 0);
   return util.getLikelihoodForState(Eigen::Vector3f(pose_map[0], pose_map[1], pose_map[2]), dc);
+}
+
+// OccGridMapUtil::getCovarianceForPose — map/OccGridMapUtil.h:106-160 (sigma points in the level's cells) and
+// getCovMatrixWorldCoords — :162-187.  The function prints its likelihoods to std::cout (:139): silenced for the call.
+void hsref_covariance_for_pose(void* hv, int level, const float pose_map[3], const float* pts_level, int n, float out_map[9],
+                               float out_world[9]) {
+  Handle* h = static_cast<Handle*>(hv);
+  hectorslam::GridMap& g = h->proc->grid(level);
+  hectorslam::OccGridMapUtilConfig<hectorslam::GridMap> util(&g);
+  hectorslam::DataContainer dc;
+  fill(dc, pts_level, n, 0);
+  std::streambuf* saved = std::cout.rdbuf(&g_nullbuf);
+  Eigen::Matrix3f cm = util.getCovarianceForPose(Eigen::Vector3f(pose_map[0], pose_map[1], pose_map[2]), dc);
+  std::cout.rdbuf(saved);
+  Eigen::Matrix3f cw = util.getCovMatrixWorldCoords(cm);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      out_map[3 * r + c] = cm(r, c);
+      out_world[3 * r + c] = cw(r, c);
+    }
 }
 
 // Batch of independent matches against the handle's current (frozen) map.

@@ -50,21 +50,16 @@ def timed(iters=20):
     return min(best), float(np.median(best))
 
 
-base = dict(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=1, prefetch=0, trace=0, seq=0)
+base = dict(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=0, prefetch=0, trace=0, seq=0, pace=0)
 variants = [
-    ("default (partial staging)", {}),
-    ("round-1: unstaged at one wave", dict(partial=0)),
-    ("unstaged + L2 prefetch", dict(partial=0, prefetch=1)),
-    ("partial + L2 prefetch", dict(prefetch=1)),
-    ("always fully staged", dict(stage_smem=2)),
-    ("never staged", dict(stage_smem=0)),
-    ("never staged + prefetch", dict(stage_smem=0, prefetch=1)),
-    ("unstaged U=8", dict(partial=0, unroll=8)),
-    ("partial U=8", dict(unroll=8)),
-    ("W=1 G=2 partial", dict(warps_per_scan=1, scans_per_block=2)),
-    ("W=2 G=1", dict(warps_per_scan=2, scans_per_block=1)),
-    ("W=2 G=1 unstaged", dict(warps_per_scan=2, scans_per_block=1, stage_smem=0)),
+    ("default", {}),
+    ("G=1 partial staging", dict(partial=1)),
 ]
+for G in (28, 14, 7, 2):
+    for pace in (0, 1, 2, 4):
+        for stage, part in ((0, 0), (1, 1)):
+            variants.append((f"G={G} pace={pace} " + ("staged prefix" if stage else "unstaged"),
+                             dict(warps_per_scan=1, scans_per_block=G, pace=pace, stage_smem=stage, partial=part)))
 ref = None
 for name, kw in variants:
     t = dict(base)
@@ -120,7 +115,30 @@ def timeline(label, kw):
     print("scans alive at t = 0,10,20.. us:", alive)
 
 
-timeline("default", {})
-timeline("round-1 unstaged", dict(partial=0))
+def slot_study():
+    """Which scans are slow: the same ones in two runs (data) or the same warp slots (scheduling)?"""
+    t = dict(base)
+    t["trace"] = 1
+    rep.set_tuning(**t)
+    durs, slots = [], []
+    for k in range(3):
+        run(0)
+        torch.cuda.synchronize()
+        tr = rep.read_trace(B).astype(np.int64)
+        durs.append((tr[:, 4] - tr[:, 0]) / 1e3)
+        slots.append(tr[:, 6])
+    c01 = np.corrcoef(durs[0], durs[1])[0, 1]
+    print(f"--- slot study: correlation of per-scan durations between two runs on identical inputs: {c01:.3f}")
+    d, w = durs[2], slots[2]
+    print("duration p50 by hardware warp slot (%warpid):")
+    for slot in sorted(set(w.tolist())):
+        sel = w == slot
+        print(f"  warpid {slot:2d} (scheduler {slot % 4}): n={int(sel.sum()):4d} p50 {np.median(d[sel]):6.1f} us")
+
+
+timeline("default (G=1 unstaged)", {})
+slot_study()
+timeline("G=28 pace=1 staged prefix", dict(warps_per_scan=1, scans_per_block=28, pace=1, stage_smem=1, partial=1))
+timeline("G=28 pace=0 staged prefix", dict(warps_per_scan=1, scans_per_block=28, pace=0, stage_smem=1, partial=1))
 rep.set_tuning(**base)
 rep.close()

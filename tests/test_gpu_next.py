@@ -62,6 +62,42 @@ def test_likelihood_batch(hsb_lib, pyoracle, oracle_kinds, mode):
     orc.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_covariance_batch(hsb_lib, pyoracle, oracle_kinds, mode):
+    """N3: getCovarianceForPose (OccGridMapUtil.h:106-160) + getCovMatrixWorldCoords (:162-187) against the compiled
+    reference.  The seven likelihoods differ from the sequential sum by summation order only (<= 2e-6 each); the
+    covariance is a weighted sum of squared +-1.5-cell / +-0.05-rad deviations, compared to 2e-5 of its largest entry."""
+    from hector_slam_b200 import capi
+
+    g = load_golden("match3.npz")
+    kind = "reference" if "reference" in oracle_kinds else "port"
+    orc = pyoracle.Oracle(kind, float(g["res"]), int(g["size"]), 3)
+    rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, gather_mode=mode)
+    for l, p in enumerate(golden_planes(g)):
+        rep.upload_level(l, p)
+        orc.set_logodds(l, p)
+    K = g["scans"].shape[0]
+    pts = g["scans"].reshape(-1, 2)
+    offs = (np.arange(K + 1) * g["scans"].shape[1]).astype(np.int32)
+    poses = g["ref_poses"].copy()
+    poses[5] = g["hints"][5]
+    for l in range(3):
+        cm, cw = rep.covariance_batch(l, poses, pts, offs)
+        for k in range(K):
+            wm, ww = orc.covariance_for_pose(l, orc.map_coords_pose(l, poses[k]),
+                                             (g["scans"][k] * np.float32(2.0 ** -l)).astype(np.float32))
+            assert np.abs(cm[k] - wm).max() <= 2e-5 * np.abs(wm).max(), (l, k, cm[k], wm)
+            assert np.abs(cw[k] - ww).max() <= 2e-5 * np.abs(ww).max(), (l, k)
+            assert np.array_equal(cw[k], cw[k].T)
+        assert cm[:, 0, 0].min() > 0 and cm[:, 2, 2].min() > 0
+    # shared-scan mode: B poses, one scan
+    cm1, _ = rep.covariance_batch(0, poses[:4], g["scans"][2], None)
+    wm, _ = orc.covariance_for_pose(0, orc.map_coords_pose(0, poses[1]), g["scans"][2])
+    assert np.abs(cm1[1] - wm).max() <= 2e-5 * np.abs(wm).max()
+    rep.close()
+    orc.close()
+
+
 def test_config4_best_hypothesis_by_likelihood(hsb_lib, pyoracle):
     """Config 4 end to end on one GPU: match 8192 hypotheses of one scan, score the results with the
     likelihood kernel, pick the best — it must be the in-basin fixed point (== the oracle's answer)."""
@@ -124,3 +160,52 @@ def test_raycast_batch_bit_exact(hsb_lib, pyoracle):
         assert n_hit > 100
     rep.close()
     orc.close()
+
+
+def test_raycast_and_get_dist_against_the_compiled_header(hsb_lib, pyoracle, oracle_kinds):
+    """N4 pinned on the reference itself: hector_map_tools/HectorMapTools.h compiled unmodified (oracle/maptools_driver.cpp,
+    nav_msgs stubbed) over the occupancy grid the device exports — checkOccupancyBresenhami (:148-214) cell for cell and
+    getDist (:133-147) with its world <-> map legs (CoordinateTransformer, :41-116), float for float."""
+    from hector_slam_b200 import capi
+
+    g = load_golden("match3.npz")
+    size = int(g["size"])
+    rep = capi.MapRepB200(float(g["res"]), size, levels=3)
+    port = pyoracle.Oracle("port", float(g["res"]), size, 3)
+    for l, p in enumerate(golden_planes(g)):
+        rep.upload_level(l, p)
+        port.set_logodds(l, p)
+    rng = np.random.default_rng(12)
+    have_ref = "reference" in oracle_kinds
+    for level in (0, 1):
+        s = size >> level
+        _, _, cell = rep.level_info(level)
+        origin = rep.map_origin(level)
+        assert np.array_equal(origin, port.map_origin(level))
+        B = 6000
+        half = 0.5 * s * cell
+        bw = rng.uniform(-0.5 * half, 0.5 * half, (B, 2)).astype(np.float32)
+        ew = rng.uniform(-1.05 * half, 1.05 * half, (B, 2)).astype(np.float32)      # some end outside the map
+        bw[:20] = rng.uniform(-1.2 * half, 1.2 * half, (20, 2))
+        ew[20:25] = bw[20:25]
+        bw[25] = (np.nan, 0.0)
+        dist, hit, found = rep.get_dist_batch(level, bw, ew)
+        begin = rng.integers(int(0.3 * s), int(0.7 * s), (B, 2)).astype(np.int32)
+        end = rng.integers(-5, s + 5, (B, 2)).astype(np.int32)
+        cdist, chit = rep.raycast_batch(level, begin, end)
+        mt = pyoracle.RefMapTools(rep.download_occupancy(level), cell, origin) if have_ref else None
+        nfound = 0
+        for b in range(0, B, 3):
+            if b != 25:
+                d, hw, f = mt.get_dist(bw[b], ew[b]) if have_ref else port.get_dist(level, bw[b], ew[b])
+                assert dist[b] == np.float32(d) and found[b] == f, (level, b, dist[b], d)
+                if f:
+                    assert np.array_equal(hit[b], hw), (level, b, hit[b], hw)
+                    nfound += 1
+            d, h = mt.raycast(begin[b], end[b]) if have_ref else port.raycast(level, begin[b], end[b])
+            assert cdist[b] == d and tuple(chit[b]) == h, (level, b)
+        assert nfound > 200 and not found[25] and dist[25] == np.float32(-cell)
+        if mt:
+            mt.close()
+    rep.close()
+    port.close()

@@ -209,3 +209,40 @@ def test_reference_sensitivity_on_a_sparse_map(pyoracle, oracle_kinds):
     assert np.median(order) <= 1e-6                         # most steps: order does not matter at all
     assert max(order.max(), hintsens.max()) >= 1e-4         # some steps: the reference itself moves past the bar
     assert max(order.max(), hintsens.max()) <= 2e-3         # ... but not arbitrarily far
+
+
+def test_covariance_and_map_tools_port_equals_reference(pyoracle, oracle_kinds):
+    """The "next" rows the port restates — sigma-point covariance (OccGridMapUtil.h:106-187) and hector_map_tools'
+    ray cast / getDist (HectorMapTools.h:133-237) — against the reference headers compiled in oracle/_ref: bit-exact."""
+    if "reference" not in oracle_kinds:
+        pytest.skip("oracle/_ref not built here")
+    g = load_golden("match3.npz")
+    port, ref = make(pyoracle, "port", g), make(pyoracle, "reference", g)
+    set_planes(port, golden_planes(g))
+    set_planes(ref, golden_planes(g))
+    for k in range(0, g["scans"].shape[0], 3):
+        for l in range(int(g["levels"])):
+            pm = port.map_coords_pose(l, g["ref_poses"][k])
+            pts = (g["scans"][k] * np.float32(2.0 ** -l)).astype(np.float32)
+            a, b = port.covariance_for_pose(l, pm, pts), ref.covariance_for_pose(l, pm, pts)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            assert a[0][0, 0] > 0 and np.array_equal(a[1], a[1].T)
+    rng = np.random.default_rng(0)
+    size = int(g["size"])
+    for l in range(int(g["levels"])):
+        lo = port.get_logodds(l)
+        occ = np.where(lo < 0, 0, np.where(lo > 0, 100, -1)).astype(np.int8)   # publishMap, HectorMappingRos.cpp:448-468
+        mt = pyoracle.RefMapTools(occ, port.cell_length(l), port.map_origin(l))
+        s = size >> l
+        hits = 0
+        for _ in range(1500):
+            b, e = rng.integers(-5, s + 5, 2), rng.integers(-5, s + 5, 2)
+            assert port.raycast(l, b, e) == mt.raycast(b, e)
+            bw, ew = rng.uniform(-14, 14, 2).astype(np.float32), rng.uniform(-14, 14, 2).astype(np.float32)
+            a, r = port.get_dist(l, bw, ew), mt.get_dist(bw, ew)
+            assert a[0] == r[0] and a[2] == r[2] and np.array_equal(a[1], r[1])
+            hits += a[2]
+        assert hits > 50
+        mt.close()
+    port.close()
+    ref.close()
