@@ -24,14 +24,15 @@ EXPORTED = [
     "hsb_map_coords_pose", "hsb_world_coords_pose", "hsb_match_data", "hsb_match_batch", "hsb_match_batch_device",
     "hsb_hessian_derivs", "hsb_update_by_scan", "hsb_update_level_by_scan", "hsb_on_map_updated",
     "hsb_set_map_update_min_dist_diff", "hsb_set_map_update_min_angle_diff", "hsb_slam_update",
-    "hsb_get_last_map_update_pose",
+    "hsb_get_last_map_update_pose", "hsb_set_last_map_update_pose",
     "hsb_upload_level", "hsb_download_level", "hsb_download_prob", "hsb_level_logodds_device_ptr",
     "hsb_refresh_level", "hsb_last_error", "hsb_status_string", "hsb_get_launch_count", "hsb_get_gather_mode",
     "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
     "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch",
     "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device", "hsb_raycast_batch",
     "hsb_read_trace", "hsb_get_last_launch_shape",
-    "hsb_covariance_batch", "hsb_get_map_origin", "hsb_get_dist_batch", "hsb_set_cloud_format", "hsb_cloud_to_points", "hsb_match_batch_cloud", "hsb_match_batch_cloud_device",
+    "hsb_get_dirty_rects", "hsb_get_mirror_dirty_rect", "hsb_download_level_rect", "hsb_download_occupancy_rect",
+    "hsb_get_d2h_bytes", "hsb_covariance_batch", "hsb_get_map_origin", "hsb_get_dist_batch", "hsb_set_cloud_format", "hsb_cloud_to_points", "hsb_match_batch_cloud", "hsb_match_batch_cloud_device",
 ]
 
 
@@ -110,6 +111,7 @@ def load_library() -> C.CDLL:
     sig("hsb_set_map_update_min_angle_diff", i, vp, f)
     sig("hsb_slam_update", i, vp, vp, vp, i, vp, i, vp, vp, vp)
     sig("hsb_get_last_map_update_pose", i, vp, vp)
+    sig("hsb_set_last_map_update_pose", i, vp, vp)
     sig("hsb_upload_level", i, vp, i, vp)
     sig("hsb_download_level", i, vp, i, vp)
     sig("hsb_download_prob", i, vp, i, vp)
@@ -131,6 +133,11 @@ def load_library() -> C.CDLL:
     sig("hsb_get_map_origin", i, vp, i, vp)
     sig("hsb_get_dist_batch", i, vp, i, i, vp, vp, vp, vp, vp)
     sig("hsb_get_dirty_rect", i, vp, i, vp, i)
+    sig("hsb_get_dirty_rects", i, vp, vp, i)
+    sig("hsb_get_mirror_dirty_rect", i, vp, i, vp, i)
+    sig("hsb_download_level_rect", i, vp, i, vp, vp)
+    sig("hsb_download_occupancy_rect", i, vp, i, vp, vp)
+    sig("hsb_get_d2h_bytes", C.c_uint64, vp)
     sig("hsb_raycast_batch", i, vp, i, i, vp, vp, vp, vp)
     sig("hsb_set_cloud_format", i, vp, C.POINTER(HsbCloudFormat))
     sig("hsb_cloud_to_points", i, vp, vp, i, vp, ip, vp)
@@ -534,6 +541,38 @@ class MapRepB200:
         self._check(self.lib.hsb_get_dirty_rect(self.h, level, r, int(reset)))
         rect = tuple(int(v) for v in r)
         return None if rect[2] < rect[0] else rect
+
+    def get_dirty_rects(self, reset: bool = False):
+        """All levels' replication rectangles with one copy: list of (x0, y0, x1, y1) or None."""
+        r = (C.c_int * (4 * self.levels))()
+        self._check(self.lib.hsb_get_dirty_rects(self.h, r, int(reset)))
+        out = []
+        for l in range(self.levels):
+            rect = tuple(int(v) for v in r[4 * l:4 * l + 4])
+            out.append(None if rect[2] < rect[0] else rect)
+        return out
+
+    def get_mirror_dirty_rect(self, level: int, reset: bool = False):
+        r = (C.c_int * 4)()
+        self._check(self.lib.hsb_get_mirror_dirty_rect(self.h, level, r, int(reset)))
+        rect = tuple(int(v) for v in r)
+        return None if rect[2] < rect[0] else rect
+
+    def download_level_rect(self, level: int, rect) -> np.ndarray:
+        w, hgt = rect[2] - rect[0] + 1, rect[3] - rect[1] + 1
+        out = np.zeros((hgt, w), np.float32)
+        self._check(self.lib.hsb_download_level_rect(self.h, level, (C.c_int * 4)(*rect), out.ctypes.data))
+        return out
+
+    def download_occupancy_rect(self, level: int, rect) -> np.ndarray:
+        w, hgt = rect[2] - rect[0] + 1, rect[3] - rect[1] + 1
+        out = np.zeros((hgt, w), np.int8)
+        self._check(self.lib.hsb_download_occupancy_rect(self.h, level, (C.c_int * 4)(*rect), out.ctypes.data))
+        return out
+
+    @property
+    def d2h_bytes(self) -> int:
+        return int(self.lib.hsb_get_d2h_bytes(self.h))
 
     def pack_rect_device(self, level: int, rect, d_buf: int, stream: int = 0):
         r = (C.c_int * 4)(*rect)

@@ -31,7 +31,9 @@ struct Level {
   cudaTextureObject_t tex = 0;
   cudaSurfaceObject_t surf = 0;
   int evals = 0;
-  int* dirty = nullptr;  // device {xmin, ymin, xmax, ymax}
+  int* dirty = nullptr;  // device: two rectangles {xmin, ymin, xmax, ymax} of cells written since their last reset —
+                         // [0..3] for replication (hsb_get_dirty_rect), [4..7] for host mirrors (hsb_get_mirror_dirty_rect);
+                         // points into hsb_handle::d_dirty_all
 };
 
 struct DevBuf {
@@ -72,6 +74,9 @@ struct hsb_handle {
   float* h_pin_dev = nullptr;    // device alias of h_pin
   int shape_batch = 0;           // > 0: pick the launch shape for this batch size instead of the launch's own (pipelined host calls)
   int tune_host_out = 1;         // single-scan calls: kernels write results into mapped host memory (no D2H copy)
+  int* d_dirty_all = nullptr;   // HSB_MAX_LEVELS x 8 ints, see Level::dirty
+  uint64_t d2h_bytes = 0;       // bytes the plane / rectangle download entry points copied to the host (diagnostic)
+  cudaEvent_t ev_sync[4] = {nullptr, nullptr, nullptr, nullptr};   // ordering of caller streams against the handle's own
   DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
   float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
@@ -173,6 +178,21 @@ int refresh_level(hsb_handle* h, int level, cudaStream_t st) {
   return HSB_OK;
 }
 
+int check_rect(hsb_handle* h, const Level& L, const int rect[4]) {
+  if (rect[0] < 0 || rect[1] < 0 || rect[2] >= L.sx || rect[3] >= L.sy || rect[2] < rect[0] || rect[3] < rect[1])
+    return fail(h, HSB_ERR_INVALID_ARG, "rectangle outside the level or empty");
+  return HSB_OK;
+}
+
+// both dirty rectangles of a level := the whole level (after a reset or an upload every cell may differ)
+int mark_level_dirty(hsb_handle* h, int level, cudaStream_t st) {
+  Level& L = h->lv[level];
+  if (!L.dirty) return HSB_OK;
+  const int full[8] = {0, 0, L.sx - 1, L.sy - 1, 0, 0, L.sx - 1, L.sy - 1};
+  HSB_CUDA(h, cudaMemcpyAsync(L.dirty, full, sizeof(full), cudaMemcpyHostToDevice, st));
+  return HSB_OK;
+}
+
 int clear_level(hsb_handle* h, int level, cudaStream_t st) {
   Level& L = h->lv[level];
   size_t n = (size_t)L.sx * L.sy;
@@ -181,11 +201,7 @@ int clear_level(hsb_handle* h, int level, cudaStream_t st) {
   h->launches++;
   HSB_CUDA(h, cudaGetLastError());
   L.stamp_base = 0;
-  if (L.dirty) {
-    const int clean[4] = {INT_MAX, INT_MAX, -1, -1};
-    HSB_CUDA(h, cudaMemcpyAsync(L.dirty, clean, sizeof(clean), cudaMemcpyHostToDevice, st));
-  }
-  return HSB_OK;
+  return mark_level_dirty(h, level, st);   // every cell changed: replicas / mirrors must see the whole level
 }
 
 void fill_level_dev(const hsb_handle* h, int l, HsbLevelDev& d) {
@@ -381,7 +397,6 @@ int destroy_level(hsb_handle* h, Level& L) {
   if (L.logodds) cudaFree(L.logodds);
   if (L.prob) cudaFree(L.prob);
   if (L.stamp) cudaFree(L.stamp);
-  if (L.dirty) cudaFree(L.dirty);
   L = Level();
   (void)h;
   return HSB_OK;
@@ -478,6 +493,8 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
   HSB_CUDA_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->ev_sync[i], cudaEventDisableTiming));
+  HSB_CUDA_C(cudaMalloc(&h->d_dirty_all, HSB_MAX_LEVELS * 8 * sizeof(int)));
   HSB_CUDA_C(cudaHostAlloc(&h->h_pin, 64 * sizeof(float), cudaHostAllocMapped));
   HSB_CUDA_C(cudaHostGetDevicePointer(&h->h_pin_dev, h->h_pin, 0));
 
@@ -517,11 +534,7 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
     HSB_CUDA_C(cudaMalloc(&L.logodds, n * sizeof(float)));
     HSB_CUDA_C(cudaMalloc(&L.prob, n * sizeof(float)));
     HSB_CUDA_C(cudaMalloc(&L.stamp, n * sizeof(uint32_t)));
-    HSB_CUDA_C(cudaMalloc(&L.dirty, 4 * sizeof(int)));
-    {
-      const int clean[4] = {INT_MAX, INT_MAX, -1, -1};
-      HSB_CUDA_C(cudaMemcpy(L.dirty, clean, sizeof(clean), cudaMemcpyHostToDevice));
-    }
+    L.dirty = h->d_dirty_all + 8 * l;
     if (h->gather_mode == HSB_GATHER_TEX) {
       cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
       HSB_CUDA_C(cudaMallocArray(&L.arr, &desc, dx, dy, cudaArrayTextureGather | cudaArraySurfaceLoadStore));
@@ -544,6 +557,11 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
     dy /= 2;
     res *= 2.0f;  // :68
   }
+  {
+    int clean[HSB_MAX_LEVELS * 8];
+    for (int i = 0; i < HSB_MAX_LEVELS * 8; ++i) clean[i] = (i & 2) ? -1 : INT_MAX;
+    HSB_CUDA_C(cudaMemcpyAsync(h->d_dirty_all, clean, sizeof(clean), cudaMemcpyHostToDevice, h->stream));
+  }
   HSB_CUDA_C(cudaStreamSynchronize(h->stream));
 #undef HSB_TRY
 #undef HSB_CUDA_C
@@ -561,6 +579,9 @@ int hsb_destroy(hsb_handle* h) {
                     &h->d_cloud, &h->d_cloud_off, &h->d_cloud_tf, &h->d_origo};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  if (h->d_dirty_all) cudaFree(h->d_dirty_all);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev_sync[i]) cudaEventDestroy(h->ev_sync[i]);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (int i = 0; i < 4; ++i)
@@ -1219,6 +1240,17 @@ int hsb_slam_update(hsb_handle* h, const float hint[3], const float* pts, int n,
   return HSB_OK;
 }
 
+int hsb_set_last_map_update_pose(hsb_handle* h, const float pose[3]) {
+  if (!h || !pose) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int s = ensure(h, h->d_gate, 4 * sizeof(float));
+  if (s != HSB_OK) return s;
+  memcpy(h->h_pin + 56, pose, 3 * sizeof(float));
+  HSB_CUDA(h, cudaMemcpyAsync(h->d_gate.p, h->h_pin + 56, 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HSB_OK;
+}
+
 int hsb_get_last_map_update_pose(hsb_handle* h, float out[3]) {
   if (!h || !out) return HSB_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
@@ -1274,6 +1306,7 @@ int hsb_upload_level(hsb_handle* h, int level, const float* logodds_host) {
   HSB_CUDA(h, cudaMemcpyAsync(L.logodds, logodds_host, (size_t)L.sx * L.sy * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   int s = refresh_level(h, level, h->stream);
   if (s != HSB_OK) return s;
+  if ((s = mark_level_dirty(h, level, h->stream)) != HSB_OK) return s;
   HSB_CUDA(h, cudaStreamSynchronize(h->stream));
   return HSB_OK;
 }
@@ -1284,8 +1317,44 @@ int hsb_download_level(hsb_handle* h, int level, float* out) {
   Level& L = h->lv[level];
   HSB_CUDA(h, cudaMemcpyAsync(out, L.logodds, (size_t)L.sx * L.sy * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->d2h_bytes += (size_t)L.sx * L.sy * sizeof(float);
   return HSB_OK;
 }
+
+int hsb_download_level_rect(hsb_handle* h, int level, const int rect[4], float* out) {
+  if (!h || level < 0 || level >= h->levels || !rect || !out) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  int s = check_rect(h, L, rect);
+  if (s != HSB_OK) return s;
+  const size_t w = (size_t)(rect[2] - rect[0] + 1), hgt = (size_t)(rect[3] - rect[1] + 1);
+  HSB_CUDA(h, cudaMemcpy2DAsync(out, w * sizeof(float), L.logodds + (size_t)rect[1] * L.sx + rect[0], (size_t)L.sx * sizeof(float),
+                                w * sizeof(float), hgt, cudaMemcpyDeviceToHost, h->stream));
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->d2h_bytes += w * hgt * sizeof(float);
+  return HSB_OK;
+}
+
+int hsb_download_occupancy_rect(hsb_handle* h, int level, const int rect[4], int8_t* out) {
+  if (!h || level < 0 || level >= h->levels || !rect || !out) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  Level& L = h->lv[level];
+  int s = check_rect(h, L, rect);
+  if (s != HSB_OK) return s;
+  const int w = rect[2] - rect[0] + 1, hgt = rect[3] - rect[1] + 1;
+  const size_t n = (size_t)w * hgt;
+  if ((s = ensure(h, h->d_occ, n)) != HSB_OK) return s;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  hsb::occupancy_rect_kernel<<<blocks, 256, 0, h->stream>>>(L.logodds, L.sx, rect[0], rect[1], w, hgt, static_cast<int8_t*>(h->d_occ.p));
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  HSB_CUDA(h, cudaMemcpyAsync(out, h->d_occ.p, n, cudaMemcpyDeviceToHost, h->stream));
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->d2h_bytes += n;
+  return HSB_OK;
+}
+
+uint64_t hsb_get_d2h_bytes(const hsb_handle* h) { return h ? h->d2h_bytes : 0; }
 
 int hsb_download_prob(hsb_handle* h, int level, float* out) {
   if (!h || level < 0 || level >= h->levels || !out) return HSB_ERR_INVALID_ARG;
@@ -1314,6 +1383,7 @@ int hsb_download_occupancy(hsb_handle* h, int level, int8_t* out) {
   HSB_CUDA(h, cudaGetLastError());
   HSB_CUDA(h, cudaMemcpyAsync(out, h->d_occ.p, n, cudaMemcpyDeviceToHost, h->stream));
   HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->d2h_bytes += n;
   return HSB_OK;
 }
 
@@ -1391,23 +1461,63 @@ int hsb_covariance_batch(hsb_handle* h, int level, int B, const float* poses, co
   return HSB_OK;
 }
 
-int hsb_get_dirty_rect(hsb_handle* h, int level, int rect[4], int reset) {
+static int get_dirty(hsb_handle* h, int level, int which, int rect[4], int reset) {
   if (!h || level < 0 || level >= h->levels || !rect) return HSB_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
   Level& L = h->lv[level];
-  HSB_CUDA(h, cudaMemcpyAsync(rect, L.dirty, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int* src = L.dirty + 4 * which;
+  int* pin = reinterpret_cast<int*>(h->h_pin + 60);
+  HSB_CUDA(h, cudaMemcpyAsync(pin, src, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (reset) {
-    const int clean[4] = {INT_MAX, INT_MAX, -1, -1};
-    HSB_CUDA(h, cudaMemcpyAsync(L.dirty, clean, sizeof(clean), cudaMemcpyHostToDevice, h->stream));
+    static const int clean[4] = {INT_MAX, INT_MAX, -1, -1};
+    HSB_CUDA(h, cudaMemcpyAsync(src, clean, sizeof(clean), cudaMemcpyHostToDevice, h->stream));
+  }
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  memcpy(rect, pin, 4 * sizeof(int));
+  return HSB_OK;
+}
+int hsb_get_dirty_rect(hsb_handle* h, int level, int rect[4], int reset) { return get_dirty(h, level, 0, rect, reset); }
+int hsb_get_mirror_dirty_rect(hsb_handle* h, int level, int rect[4], int reset) { return get_dirty(h, level, 1, rect, reset); }
+
+// All levels' replication rectangles with one copy and one synchronize (levels x 4 ints).
+int hsb_get_dirty_rects(hsb_handle* h, int* rects, int reset) {
+  if (!h || !rects) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int all[HSB_MAX_LEVELS * 8];
+  HSB_CUDA(h, cudaMemcpyAsync(all, h->d_dirty_all, sizeof(all), cudaMemcpyDeviceToHost, h->stream));
+  HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int l = 0; l < h->levels; ++l) memcpy(rects + 4 * l, all + 8 * l, 4 * sizeof(int));
+  if (reset) {
+    for (int l = 0; l < h->levels; ++l) {
+      all[8 * l + 0] = all[8 * l + 1] = INT_MAX;
+      all[8 * l + 2] = all[8 * l + 3] = -1;
+    }
+    HSB_CUDA(h, cudaMemcpyAsync(h->d_dirty_all, all, sizeof(all), cudaMemcpyHostToDevice, h->stream));
     HSB_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   return HSB_OK;
 }
 
-static int check_rect(hsb_handle* h, const Level& L, const int rect[4]) {
-  if (rect[0] < 0 || rect[1] < 0 || rect[2] >= L.sx || rect[3] >= L.sy || rect[2] < rect[0] || rect[3] < rect[1])
-    return fail(h, HSB_ERR_INVALID_ARG, "rectangle outside the level or empty");
+// Stream ordering of the rectangle transport: the handle's own work runs on private non-blocking
+// streams (h->stream for map writes and single-scan calls, copy_stream[] for the host-buffer batch calls), the
+// caller's `stream` is a different one.  pack: reads the log-odds after everything queued on h->stream, and the next
+// map write waits for the read.  unpack: writes log-odds / probabilities / texture twin after everything queued on
+// the handle's streams (earlier matches may still be reading them), and whatever the handle queues next waits for it.
+static int order_before(hsb_handle* h, cudaStream_t user, bool all_streams) {
+  HSB_CUDA(h, cudaEventRecord(h->ev_sync[0], h->stream));
+  HSB_CUDA(h, cudaStreamWaitEvent(user, h->ev_sync[0], 0));
+  if (all_streams)
+    for (int i = 0; i < 2; ++i) {
+      HSB_CUDA(h, cudaEventRecord(h->ev_sync[1 + i], h->copy_stream[i]));
+      HSB_CUDA(h, cudaStreamWaitEvent(user, h->ev_sync[1 + i], 0));
+    }
+  return HSB_OK;
+}
+static int order_after(hsb_handle* h, cudaStream_t user, bool all_streams) {
+  HSB_CUDA(h, cudaEventRecord(h->ev_sync[3], user));
+  HSB_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_sync[3], 0));
+  if (all_streams)
+    for (int i = 0; i < 2; ++i) HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[i], h->ev_sync[3], 0));
   return HSB_OK;
 }
 
@@ -1420,10 +1530,11 @@ int hsb_pack_rect_device(hsb_handle* h, int level, const int rect[4], float* d_b
   const int w = rect[2] - rect[0] + 1, hgt = rect[3] - rect[1] + 1;
   const size_t n = (size_t)w * hgt;
   int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  if ((s = order_before(h, (cudaStream_t)stream, false)) != HSB_OK) return s;
   hsb::pack_rect_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(L.logodds, L.sx, rect[0], rect[1], w, hgt, d_buf);
   h->launches++;
   HSB_CUDA(h, cudaGetLastError());
-  return HSB_OK;
+  return order_after(h, (cudaStream_t)stream, false);
 }
 
 int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const float* d_buf, void* stream) {
@@ -1435,11 +1546,12 @@ int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const fl
   const int w = rect[2] - rect[0] + 1, hgt = rect[3] - rect[1] + 1;
   const size_t n = (size_t)w * hgt;
   int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 16);
+  if ((s = order_before(h, (cudaStream_t)stream, true)) != HSB_OK) return s;
   hsb::unpack_rect_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(L.logodds, L.prob, L.surf, L.sx, rect[0], rect[1], w, hgt,
-                                                                    d_buf);
+                                                                    d_buf, L.dirty + 4);
   h->launches++;
   HSB_CUDA(h, cudaGetLastError());
-  return HSB_OK;
+  return order_after(h, (cudaStream_t)stream, true);
 }
 
 int hsb_raycast_batch(hsb_handle* h, int level, int B, const int* begin_cells, const int* end_cells, float* out_dist,

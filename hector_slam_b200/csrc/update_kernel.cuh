@@ -74,6 +74,17 @@ __global__ void occupancy_kernel(const float* __restrict__ logodds, int8_t* __re
   }
 }
 
+// N1 on a rectangle: the cells of {x0, y0, w, hgt} thresholded into a packed w x hgt buffer (dirty-rectangle publishing).
+__global__ void occupancy_rect_kernel(const float* __restrict__ logodds, int sx, int x0, int y0, int w, int hgt,
+                                      int8_t* __restrict__ out) {
+  const size_t n = (size_t)w * hgt;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (size_t)w), c = (int)(i - (size_t)r * w);
+    const float l = logodds[(size_t)(y0 + r) * sx + (x0 + c)];
+    out[i] = l < 0.0f ? (int8_t)0 : (l > 0.0f ? (int8_t)100 : (int8_t)-1);
+  }
+}
+
 // N4: DistanceMeasurementProvider::checkOccupancyBresenhami (HectorMapTools.h:148-214, bresenham2D :216-237), one warp
 // per ray.  Same closed-form line as K2; 32 cells are tested per step and the first occupied one wins.
 __device__ __forceinline__ float warp_raycast(const float* __restrict__ logodds, int sx, int sy, int2 p0, int2 p1, int lane,
@@ -352,11 +363,11 @@ __global__ void __launch_bounds__(256) update_apply_kernel(const __grid_constant
   for (int k = 0; k < nw; ++k) {
     bx0 = min(bx0, red[0][k]); by0 = min(by0, red[1][k]); bx1 = max(bx1, red[2][k]); by1 = max(by1, red[3][k]);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && L.dirty) {
-    atomicMin(L.dirty + 0, bx0);
-    atomicMin(L.dirty + 1, by0);
-    atomicMax(L.dirty + 2, bx1);
-    atomicMax(L.dirty + 3, by1);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && L.dirty) {   // both rectangles: replication [0..3] and host mirror [4..7]
+    atomicMin(L.dirty + 0, bx0); atomicMin(L.dirty + 4, bx0);
+    atomicMin(L.dirty + 1, by0); atomicMin(L.dirty + 5, by0);
+    atomicMax(L.dirty + 2, bx1); atomicMax(L.dirty + 6, bx1);
+    atomicMax(L.dirty + 3, by1); atomicMax(L.dirty + 7, by1);
   }
   const float lf = P.log_odds_free, lo = P.log_odds_occ;
   const unsigned nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -408,9 +419,16 @@ __global__ void pack_rect_kernel(const float* __restrict__ logodds, int sx, int 
     buf[i] = logodds[(size_t)(y0 + r) * sx + (x0 + c)];
   }
 }
+// (a replica's host mirror has to follow too: the rectangle is folded into the level's mirror rectangle)
 __global__ void unpack_rect_kernel(float* __restrict__ logodds, float* __restrict__ prob, cudaSurfaceObject_t surf, int sx,
-                                   int x0, int y0, int w, int hgt, const float* __restrict__ buf) {
+                                   int x0, int y0, int w, int hgt, const float* __restrict__ buf, int* mirror_dirty) {
   const size_t n = (size_t)w * hgt;
+  if (mirror_dirty && blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicMin(mirror_dirty + 0, x0);
+    atomicMin(mirror_dirty + 1, y0);
+    atomicMax(mirror_dirty + 2, x0 + w - 1);
+    atomicMax(mirror_dirty + 3, y0 + hgt - 1);
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / (size_t)w), c = (int)(i - (size_t)r * w);
     const size_t off = (size_t)(y0 + r) * sx + (x0 + c);

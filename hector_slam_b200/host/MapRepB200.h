@@ -77,6 +77,8 @@ class MapRepB200 : public MapRepresentationInterface {
     check(hsb_reset(handle_));
     for (size_t i = 0; i < mirrors_.size(); ++i) {
       mirrors_[i]->reset();
+      int rect[4];
+      check(hsb_get_mirror_dirty_rect(handle_, static_cast<int>(i), rect, 1));  // mirror and device are both empty now
       stale_[i] = false;
       pending_updates_[i] = 0;
     }
@@ -90,11 +92,21 @@ class MapRepB200 : public MapRepresentationInterface {
   virtual const GridMap& getGridMap(int mapLevel) const {
     std::lock_guard<std::mutex> g(api_);
     if (stale_[mapLevel]) {
+      // only what was written since the last look travels: the device keeps a dirty rectangle per level for the host
+      // mirror (K2's apply phase folds each scan's bounding box into it), so the bytes copied under the level's
+      // mutex are proportional to the touched area, not to the map (the reference's publisher walks
+      // the whole grid under that mutex, HectorMappingRos.cpp:453-475)
       GridMap& m = *mirrors_[mapLevel];
-      const int n = m.getSizeX() * m.getSizeY();
-      scratch_.resize(static_cast<size_t>(n));
-      check(hsb_download_level(handle_, mapLevel, scratch_.data()));
-      for (int i = 0; i < n; ++i) m.getCell(i).logOddsVal = scratch_[static_cast<size_t>(i)];
+      int rect[4];
+      check(hsb_get_mirror_dirty_rect(handle_, mapLevel, rect, 1));
+      if (rect[2] >= rect[0]) {
+        const int w = rect[2] - rect[0] + 1, hgt = rect[3] - rect[1] + 1, sx = m.getSizeX();
+        scratch_.resize(static_cast<size_t>(w) * static_cast<size_t>(hgt));
+        check(hsb_download_level_rect(handle_, mapLevel, rect, scratch_.data()));
+        for (int r = 0; r < hgt; ++r)
+          for (int c = 0; c < w; ++c)
+            m.getCell((rect[1] + r) * sx + rect[0] + c).logOddsVal = scratch_[static_cast<size_t>(r) * w + c];
+      }
       for (int k = 0; k < pending_updates_[mapLevel]; ++k) m.setUpdated();  // GridMapBase.h:322
       pending_updates_[mapLevel] = 0;
       stale_[mapLevel] = false;

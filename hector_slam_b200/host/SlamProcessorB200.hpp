@@ -78,6 +78,7 @@ class SlamProcessor {
       check(hsb_update_by_scan(h_, points_xy, n, origo, p));  // :91
       check(hsb_on_map_updated(h_));                          // :93
       lastMapUpdatePose_ = newPose;                           // :94
+      check(hsb_set_last_map_update_pose(h_, p));             // keep the fused path's gate state in step (mixing allowed)
     }
   }
 

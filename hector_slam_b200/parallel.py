@@ -144,34 +144,50 @@ def match_sharded(match_fn, hints, pts, offsets, group=None, device="cpu"):
     return gather_rows(poses_t, B, group), gather_rows(cov_t, B, group).reshape(B, 3, 3)
 
 
-def broadcast_dirty_tiles(rep, device, src: int = 0, group=None) -> int:
-    """After the owner rank (`src`) has written its map (hsb_update_by_scan), ship what changed to
-    the replicas: per level the dirty rectangle (4 ints) and its log-odds rows (one broadcast
-    each); replicas write the rows into their planes and refresh the probabilities there.
-    Returns the number of cells shipped.  No-op without a process group."""
+def broadcast_dirty_tiles(rep, device, src: int = 0, group=None, stats: dict | None = None) -> int:
+    """After the owner rank (`src`) has written its map (hsb_update_by_scan / hsb_slam_update), ship what changed to
+    the replicas.  Two collectives per call, whatever the number of levels: the dirty rectangles of ALL levels (levels x 4
+    int32, read from the owner's device with one copy) and ONE packed buffer holding the log-odds rows of every
+    level's rectangle back to back; replicas write the rows into their planes and refresh the probabilities (and the
+    texture twin) there.  pack / unpack are ordered against the handle's own streams inside the C-ABI (see
+    hsb_pack_rect_device), so the caller needs no synchronisation before the next match or map write.
+    Returns the number of cells shipped.  `stats` (optional dict) receives "cells", "bytes".  No-op without a
+    process group (the rectangles are still reset)."""
+    levels = rep.getMapLevels()
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        for l in range(rep.getMapLevels()):
-            rep.get_dirty_rect(l, reset=True)
+        rep.get_dirty_rects(reset=True)
         return 0
     rank = dist.get_rank(group)
-    shipped = 0
-    stream = torch.cuda.current_stream(device).cuda_stream if torch.device(device).type == "cuda" else 0
-    for l in range(rep.getMapLevels()):
-        rect_t = torch.tensor([0, 0, -1, -1], dtype=torch.int32, device=device)  # clean: x1 < x0
-        if rank == src:
-            r = rep.get_dirty_rect(l, reset=True)
-            if r is not None:
-                rect_t = torch.tensor(r, dtype=torch.int32, device=device)
-        dist.broadcast(rect_t, src=src, group=group)
-        rect = [int(v) for v in rect_t.tolist()]
-        if rect[2] < rect[0]:
-            continue
-        n = (rect[2] - rect[0] + 1) * (rect[3] - rect[1] + 1)
-        buf = torch.empty(n, dtype=torch.float32, device=device)
-        if rank == src:
-            rep.pack_rect_device(l, rect, buf.data_ptr(), stream)
-        dist.broadcast(buf, src=src, group=group)
-        if rank != src:
-            rep.unpack_rect_device(l, rect, buf.data_ptr(), stream)
-        shipped += n
-    return shipped
+    on_gpu = torch.device(device).type == "cuda"
+    stream = torch.cuda.current_stream(device).cuda_stream if on_gpu else 0
+    rects_t = torch.empty(levels * 4, dtype=torch.int32, device=device)
+    if rank == src:
+        flat = []
+        for r in rep.get_dirty_rects(reset=True):
+            flat.extend(r if r is not None else (0, 0, -1, -1))       # clean: x1 < x0
+        rects_t.copy_(torch.tensor(flat, dtype=torch.int32))
+    dist.broadcast(rects_t, src=src, group=group)
+    rects = rects_t.cpu().view(levels, 4).tolist()
+    sizes = [max(0, r[2] - r[0] + 1) * max(0, r[3] - r[1] + 1) for r in rects]
+    total = int(sum(sizes))
+    if stats is not None:
+        stats["cells"], stats["bytes"] = total, 4 * total + 16 * levels
+    if total == 0:
+        return 0
+    buf = torch.empty(total, dtype=torch.float32, device=device)
+    off = 0
+    if rank == src:
+        for l, (r, n) in enumerate(zip(rects, sizes)):
+            if n:
+                rep.pack_rect_device(l, r, buf.data_ptr() + 4 * off, stream)
+            off += n
+    dist.broadcast(buf, src=src, group=group)
+    if rank != src:
+        off = 0
+        for l, (r, n) in enumerate(zip(rects, sizes)):
+            if n:
+                rep.unpack_rect_device(l, r, buf.data_ptr() + 4 * off, stream)
+            off += n
+        # `buf` may be recycled by torch's allocator as soon as this function returns: the unpack kernels were
+        # queued on torch's current stream, which is the stream the allocator tracks the block on — safe.
+    return total

@@ -219,6 +219,9 @@ int hsb_slam_update(hsb_handle* h, const float pose_hint_world[3], const float* 
                     float cov_inout[9], int* map_updated);
 /* lastMapUpdatePose of the fused step (HectorSlamProcessor.h:151) */
 int hsb_get_last_map_update_pose(hsb_handle* h, float out[3]);
+/* ... and its setter, for a host that wrote the map itself (hsb_update_by_scan) between fused steps: the gate of the
+ * next hsb_slam_update then compares against this pose, as HectorSlamProcessor.h:94 would have left it. */
+int hsb_set_last_map_update_pose(hsb_handle* h, const float pose[3]);
 
 /* MapRepresentationInterface::onMapUpdated — MapRepMultiMap.h:107-114.  The reference bumps its
  * probability-cache epoch here; on the device the probability planes are already current, so this
@@ -245,6 +248,12 @@ int hsb_refresh_level(hsb_handle* h, int level, void* stream);
  * hsb_unpack_rect_device writes such a buffer into this handle's plane and refreshes the
  * probability plane (and texture twin) of the rectangle.  Asynchronous on `stream`. */
 int hsb_get_dirty_rect(hsb_handle* h, int level, int rect[4], int reset);
+/* the same for every level with one device-to-host copy: rects = levels x 4 ints */
+int hsb_get_dirty_rects(hsb_handle* h, int* rects, int reset);
+/* Ordering: `stream` may be any stream of the caller.  pack waits for the map writes the handle has queued and the
+ * handle's next map write waits for pack; unpack waits for everything the handle has queued (matches still reading
+ * the planes) and everything the handle queues afterwards waits for unpack — no synchronisation is needed around
+ * them.  After hsb_reset / hsb_upload_level the dirty rectangle is the whole level. */
 int hsb_pack_rect_device(hsb_handle* h, int level, const int rect[4], float* d_buf, void* stream);
 int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const float* d_buf, void* stream);
 
@@ -254,6 +263,16 @@ int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const fl
  * GridMapLogOdds.h:81-84), 100 where occupied (> 0, :76-79), -1 otherwise.  Thresholded on the
  * device, so one byte per cell crosses PCIe instead of four.  out: [size_y][size_x] int8 (host). */
 int hsb_download_occupancy(hsb_handle* h, int level, int8_t* occupancy_host_out);
+/* Dirty-rectangle variants (the "dirty-rect download" of SURVEY.md N1): a second rectangle per level accumulates what
+ * was written since the HOST last looked (independent of the replication rectangle above; whole level after a reset
+ * or an upload).  hsb_download_level_rect / hsb_download_occupancy_rect copy only rect = {x0, y0, x1, y1} (inclusive),
+ * packed row by row ((x1-x0+1) * (y1-y0+1) values) — bytes over PCIe proportional to the touched area, which is what
+ * MapRepB200::getGridMap's mirror sync and a publishMap that keeps its data vector (HectorMappingRos.cpp:445) need.
+ * hsb_get_d2h_bytes: bytes the download entry points have copied to the host so far (tests assert the proportionality). */
+int hsb_get_mirror_dirty_rect(hsb_handle* h, int level, int rect[4], int reset);
+int hsb_download_level_rect(hsb_handle* h, int level, const int rect[4], float* logodds_rows_out);
+int hsb_download_occupancy_rect(hsb_handle* h, int level, const int rect[4], int8_t* occupancy_rows_out);
+uint64_t hsb_get_d2h_bytes(const hsb_handle* h);
 /* OccGridMapUtil::getLikelihoodForState — map/OccGridMapUtil.h:189-221: 1 - residual / n with
  * residual = sum_i (1 - interpMapValue(T(state) * p_i)) (an out-of-map endpoint counts 1), for B
  * poses (world frame; converted with getMapCoordsPose of `level`) against scan b of the batch

@@ -209,3 +209,67 @@ def test_raycast_and_get_dist_against_the_compiled_header(hsb_lib, pyoracle, ora
             mt.close()
     rep.close()
     port.close()
+
+
+def test_dirty_rect_downloads_move_only_the_touched_area(hsb_lib):
+    """N1 as SURVEY.md specifies it: dirty-rect int8 / log-odds download.  The mirror rectangle accumulates what K2
+    wrote since the host last looked; the rect downloads equal the corresponding window of the full downloads and move
+    bytes proportional to the window (hsb_get_d2h_bytes), not to the map."""
+    from hector_slam_b200 import capi
+
+    g = load_golden("slam3.npz")
+    rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+    for l in range(3):
+        assert rep.get_mirror_dirty_rect(l) is None          # a fresh handle is clean
+    pose = g["first_hint"]
+    for k in range(4):
+        pose, _ = rep.matchData(pose, g["scans"][k])
+        rep.updateByScan(g["scans"][k], pose)
+    for l in range(3):
+        sx, sy, _ = rep.level_info(l)
+        rect = rep.get_mirror_dirty_rect(l, reset=True)
+        assert rect is not None and rep.get_mirror_dirty_rect(l) is None
+        assert rep.get_dirty_rect(l) == rect                  # the replication rectangle is independent: still set
+        x0, y0, x1, y1 = rect
+        full, occ = rep.download_level(l), rep.download_occupancy(l)
+        assert np.all(full[:y0] == 0) and np.all(full[y1 + 1:] == 0) and np.all(full[:, :x0] == 0) and np.all(full[:, x1 + 1:] == 0)
+        b0 = rep.d2h_bytes
+        win = rep.download_level_rect(l, rect)
+        b1 = rep.d2h_bytes
+        owin = rep.download_occupancy_rect(l, rect)
+        b2 = rep.d2h_bytes
+        n = (x1 - x0 + 1) * (y1 - y0 + 1)
+        assert b1 - b0 == 4 * n and b2 - b1 == n and n < sx * sy // 2
+        assert np.array_equal(win, full[y0:y1 + 1, x0:x1 + 1]) and np.array_equal(owin, occ[y0:y1 + 1, x0:x1 + 1])
+    # after a reset / an upload every cell may differ: the rectangles are the whole level (ADVICE r01)
+    rep.reset()
+    assert rep.get_mirror_dirty_rect(0, reset=True) == (0, 0, int(g["size"]) - 1, int(g["size"]) - 1)
+    assert rep.get_dirty_rect(1, reset=True) == (0, 0, (int(g["size"]) >> 1) - 1, (int(g["size"]) >> 1) - 1)
+    rep.upload_level(2, np.ones((int(g["size"]) >> 2,) * 2, np.float32))
+    assert rep.get_dirty_rect(2) == (0, 0, (int(g["size"]) >> 2) - 1, (int(g["size"]) >> 2) - 1)
+    with pytest.raises(capi.HsbError):
+        rep.download_level_rect(0, (5, 5, 4, 9))
+    rep.close()
+
+
+def test_gate_state_survives_mixing_fused_and_host_driven_steps(hsb_lib):
+    """ADVICE r01: SlamProcessor::updateUnfused writes the map from the host; the fused step's device-side gate has to
+    learn the new lastMapUpdatePose (hsb_set_last_map_update_pose) or the next fused step decides differently."""
+    from hector_slam_b200 import capi
+
+    g = load_golden("slam3.npz")
+    rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+    rep.setMapUpdateMinDistDiff(0.4)
+    rep.setMapUpdateMinAngleDiff(0.9)
+    p0, _, upd = rep.slam_update(g["first_hint"], g["scans"][0])
+    assert upd and np.array_equal(rep.last_map_update_pose(), p0)
+    far = p0 + np.float32([1.0, 0.0, 0.0])
+    rep._check(rep.lib.hsb_set_last_map_update_pose(rep.h, far.ctypes.data))
+    assert np.array_equal(rep.last_map_update_pose(), far)
+    # a fused step near p0 is now > 0.4 m away from the recorded pose: the gate fires
+    _, _, upd2 = rep.slam_update(p0, g["scans"][1])
+    assert upd2
+    # and right after it does not
+    _, _, upd3 = rep.slam_update(rep.last_map_update_pose(), g["scans"][1])
+    assert not upd3
+    rep.close()

@@ -39,9 +39,10 @@ def test_dirty_rect_pack_unpack(hsb_lib):
             n = (x1 - x0 + 1) * (y1 - y0 + 1)
             assert n < after.size // 2                      # a tile, not the whole plane
             buf = torch.empty(n, dtype=torch.float32, device="cuda")
+            # no synchronisation around pack / unpack: the C-ABI orders the caller's stream against the handles' own
             a.pack_rect_device(l, rect, buf.data_ptr(), torch.cuda.current_stream().cuda_stream)
             b.unpack_rect_device(l, rect, buf.data_ptr(), torch.cuda.current_stream().cuda_stream)
-            torch.cuda.synchronize()
+            assert np.array_equal(b.download_level_rect(l, rect), after[y0:y1 + 1, x0:x1 + 1])
             assert np.array_equal(buf.cpu().numpy().reshape(y1 - y0 + 1, x1 - x0 + 1), after[y0:y1 + 1, x0:x1 + 1])
         pose = p
     for l in range(3):
@@ -74,12 +75,20 @@ def _worker(rank, world, port, q):
                               update_factor_occupied=0.9)
         pose = g["first_hint"]
         shipped = 0
+        probes = []
         for k in range(g["scans"].shape[0]):
             if rank == 0:                                  # the owner runs SLAM and writes the map
                 pose, _ = rep.matchData(pose, g["scans"][k])
                 rep.updateByScan(g["scans"][k], pose)
                 rep.onMapUpdated()
             shipped += parallel.broadcast_dirty_tiles(rep, dev, src=0)
+            # straight after the broadcast, no synchronize: the replica's match must already see the new tiles
+            pr, _ = rep.match_batch(g["est"][k:k + 1], g["scans"][k], None)
+            probes.append(pr[0])
+        pt = torch.from_numpy(np.asarray(probes, np.float32)).to(dev)
+        pg = [torch.empty_like(pt) for _ in range(world)]
+        dist.all_gather(pg, pt)
+        same_probe = all(bool(torch.equal(pg[0], x)) for x in pg)
         torch.cuda.synchronize()
         planes = [rep.download_level(l) for l in range(3)]
         sums = torch.tensor([float(np.abs(p).sum(dtype=np.float64)) for p in planes], dtype=torch.float64, device=dev)
@@ -94,7 +103,7 @@ def _worker(rank, world, port, q):
         gathered = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)
         same_match = all(bool(torch.equal(gathered[0], x)) for x in gathered)
-        q.put((rank, same_map, same_match, shipped, float(sums.sum().item())))
+        q.put((rank, same_map, same_match and same_probe, shipped, float(sums.sum().item())))
         rep.close()
     finally:
         dist.destroy_process_group()

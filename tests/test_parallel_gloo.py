@@ -78,6 +78,9 @@ def _worker(rank, world, port, q):
             def getMapLevels(self):
                 return 2
 
+            def get_dirty_rects(self, reset=False):
+                return [self.get_dirty_rect(l, reset) for l in range(2)]
+
             def write(self, l, x0, y0, x1, y1, v):
                 self.planes[l][y0:y1 + 1, x0:x1 + 1] = v
                 self.dirty[l] = (x0, y0, x1, y1)
@@ -103,9 +106,17 @@ def _worker(rank, world, port, q):
         fr = FakeRep()
         if rank == 0:
             fr.write(0, 3, 4, 10, 9, 1.5)      # level 1 stays clean on purpose
-        shipped = parallel.broadcast_dirty_tiles(fr, "cpu", src=0)
+        st = {}
+        shipped = parallel.broadcast_dirty_tiles(fr, "cpu", src=0, stats=st)
         ok = ok and shipped == 8 * 6 and float(fr.planes[0].sum()) == 1.5 * 48 and float(fr.planes[1].sum()) == 0.0
-        ok = ok and fr.get_dirty_rect(0) is None
+        ok = ok and fr.get_dirty_rect(0) is None and st["cells"] == 48
+        # both levels dirty: ONE packed buffer carries both rectangles back to back
+        if rank == 0:
+            fr.write(0, 0, 0, 4, 1, 2.0)
+            fr.write(1, 2, 2, 3, 5, -1.0)
+        shipped = parallel.broadcast_dirty_tiles(fr, "cpu", src=0)
+        ok = ok and shipped == 10 + 8 and float(fr.planes[1].sum()) == -8.0 and float(fr.planes[0][0:2, 0:5].sum()) == 20.0
+        ok = ok and parallel.broadcast_dirty_tiles(fr, "cpu", src=0) == 0   # nothing dirty: nothing shipped
         lo, hi = parallel.shard_range(K, rank, world)
         q.put((rank, ok, (lo, hi)))
     finally:
