@@ -30,8 +30,9 @@ EXPORTED = [
     "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
     "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch",
     "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device", "hsb_raycast_batch",
-    "hsb_read_trace", "hsb_get_last_launch_shape",
-    "hsb_get_dirty_rects", "hsb_get_mirror_dirty_rect", "hsb_download_level_rect", "hsb_download_occupancy_rect",
+    "hsb_read_trace", "hsb_get_last_launch_shape", "hsb_get_last_update_device_ms",
+    "hsb_match_batch_submit", "hsb_match_batch_ranges_submit", "hsb_match_batch_cloud_submit", "hsb_match_batch_wait",
+    "hsb_alloc_pinned", "hsb_free_pinned", "hsb_measure_h2d_gbs", "hsb_get_dirty_rects", "hsb_get_mirror_dirty_rect", "hsb_download_level_rect", "hsb_download_occupancy_rect",
     "hsb_get_d2h_bytes", "hsb_covariance_batch", "hsb_get_map_origin", "hsb_get_dist_batch", "hsb_set_cloud_format", "hsb_cloud_to_points", "hsb_match_batch_cloud", "hsb_match_batch_cloud_device",
 ]
 
@@ -143,6 +144,14 @@ def load_library() -> C.CDLL:
     sig("hsb_cloud_to_points", i, vp, vp, i, vp, ip, vp)
     sig("hsb_match_batch_cloud", i, vp, i, vp, vp, vp, vp, vp, vp, vp)
     sig("hsb_match_batch_cloud_device", i, vp, i, vp, vp, vp, i, vp, vp, vp, vp, vp)
+    sig("hsb_match_batch_submit", i, vp, i, vp, vp, vp, i, vp, vp, ip)
+    sig("hsb_match_batch_ranges_submit", i, vp, i, vp, vp, vp, vp, ip)
+    sig("hsb_match_batch_cloud_submit", i, vp, i, vp, vp, vp, vp, vp, vp, vp, ip)
+    sig("hsb_match_batch_wait", i, vp, i)
+    sig("hsb_alloc_pinned", vp, C.c_size_t)
+    sig("hsb_free_pinned", i, vp)
+    sig("hsb_measure_h2d_gbs", i, vp, vp, C.c_size_t, i, fp)
+    sig("hsb_get_last_update_device_ms", i, vp, fp)
     sig("hsb_read_trace", i, vp, vp, i)
     sig("hsb_get_last_launch_shape", i, vp, vp)
     sig("hsb_pack_rect_device", i, vp, i, vp, vp, vp)
@@ -165,6 +174,39 @@ def _ptr(a):
 def _f32(a, shape=None):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a if shape is None else a.reshape(shape)
+
+
+class PinnedArray:
+    """A numpy view of page-locked host memory from hsb_alloc_pinned (cudaHostAlloc by the calling thread)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.lib = load_library()
+        self.shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = self.lib.hsb_alloc_pinned(max(1, nbytes))
+        if not self.ptr:
+            raise MemoryError(f"hsb_alloc_pinned({nbytes}) failed")
+        buf = (C.c_char * max(1, nbytes)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.hsb_free_pinned(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pinned_copy(a: np.ndarray) -> PinnedArray:
+    p = PinnedArray(a.shape, a.dtype)
+    p.array[...] = a
+    return p
 
 
 class MapRepB200:
@@ -222,6 +264,11 @@ class MapRepB200:
         self._check(self.lib.hsb_get_last_launch_shape(self.h, out))
         return dict(zip(("warps_per_scan", "scans_per_block", "unroll", "staged_points", "grid", "resident_ctas"),
                         (int(v) for v in out)))
+
+    def last_update_device_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.hsb_get_last_update_device_ms(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def read_trace(self, max_scans: int) -> np.ndarray:
         out = np.zeros((max_scans, 8), np.uint64)
@@ -399,6 +446,36 @@ class MapRepB200:
         if want_cov:
             cov = out_cov.reshape(B, 3, 3) if isinstance(out_cov, np.ndarray) else out_cov
         return out_poses, cov
+
+    # -- submit / wait (streams of batches; buffers must stay alive and untouched until wait) --------
+    def match_batch_ranges_submit(self, hints, ranges, out_poses, out_cov=None) -> int:
+        t = C.c_int(-1)
+        self._check(self.lib.hsb_match_batch_ranges_submit(self.h, int(hints.shape[0]), _ptr(hints), _ptr(ranges),
+                                                           _ptr(out_poses), _ptr(out_cov), C.byref(t)))
+        return t.value
+
+    def match_batch_submit(self, hints, points_xy, offsets, out_poses, out_cov=None) -> int:
+        t = C.c_int(-1)
+        n_shared = 0 if offsets is not None else int(points_xy.shape[0])
+        self._check(self.lib.hsb_match_batch_submit(self.h, int(hints.shape[0]), _ptr(hints), _ptr(points_xy),
+                                                    _ptr(offsets), n_shared, _ptr(out_poses), _ptr(out_cov), C.byref(t)))
+        return t.value
+
+    def match_batch_cloud_submit(self, hints, points_xyz, offsets, out_poses, out_cov=None, out_origo=None,
+                                 transforms=None) -> int:
+        t = C.c_int(-1)
+        self._check(self.lib.hsb_match_batch_cloud_submit(self.h, int(hints.shape[0]), _ptr(hints), _ptr(points_xyz),
+                                                          _ptr(offsets), _ptr(transforms), _ptr(out_poses), _ptr(out_cov),
+                                                          _ptr(out_origo), C.byref(t)))
+        return t.value
+
+    def measure_h2d_gbs(self, host_ptr: int, nbytes: int, reps: int = 5) -> float:
+        out = C.c_float()
+        self._check(self.lib.hsb_measure_h2d_gbs(self.h, host_ptr, nbytes, reps, C.byref(out)))
+        return float(out.value)
+
+    def match_batch_wait(self, ticket: int):
+        self._check(self.lib.hsb_match_batch_wait(self.h, int(ticket)))
 
     def match_batch_ranges_device(self, B: int, d_hints: int, d_ranges: int, d_out_poses: int, d_out_cov: int | None,
                                   stream: int = 0):

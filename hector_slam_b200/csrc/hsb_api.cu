@@ -41,6 +41,12 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+struct BatchSet {
+  DevBuf hints, in, offsets, poses, cov, origo, tf;
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  bool busy = false;
+};
+
 }  // namespace
 
 struct hsb_handle {
@@ -74,6 +80,10 @@ struct hsb_handle {
   float* h_pin_dev = nullptr;    // device alias of h_pin
   int shape_batch = 0;           // > 0: pick the launch shape for this batch size instead of the launch's own (pipelined host calls)
   int tune_host_out = 1;         // single-scan calls: kernels write results into mapped host memory (no D2H copy)
+  cudaEvent_t ev_time[2] = {nullptr, nullptr};   // timing events around K2 (tuning "time_update")
+  int tune_time_update = 0;
+  BatchSet bset[2];             // device staging of the host-buffer batch calls, alternating between calls
+  int next_set = 0;
   int* d_dirty_all = nullptr;   // HSB_MAX_LEVELS x 8 ints, see Level::dirty
   uint64_t d2h_bytes = 0;       // bytes the plane / rectangle download entry points copied to the host (diagnostic)
   cudaEvent_t ev_sync[4] = {nullptr, nullptr, nullptr, nullptr};   // ordering of caller streams against the handle's own
@@ -432,6 +442,14 @@ int hsb_get_last_launch_shape(const hsb_handle* h, int out[6]) {
   return HSB_OK;
 }
 
+int hsb_get_last_update_device_ms(hsb_handle* h, float* ms) {
+  if (!h || !ms) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  HSB_CUDA(h, cudaEventSynchronize(h->ev_time[1]));
+  HSB_CUDA(h, cudaEventElapsedTime(ms, h->ev_time[0], h->ev_time[1]));
+  return HSB_OK;
+}
+
 int hsb_read_trace(hsb_handle* h, uint64_t* out, int max_scans) {
   if (!h || !out || max_scans < 0) return HSB_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
@@ -494,6 +512,9 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
   for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
   for (int i = 0; i < 4; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->ev_sync[i], cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k)
+    for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->bset[k].done[i], cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaEventCreate(&h->ev_time[i]));
   HSB_CUDA_C(cudaMalloc(&h->d_dirty_all, HSB_MAX_LEVELS * 8 * sizeof(int)));
   HSB_CUDA_C(cudaHostAlloc(&h->h_pin, 64 * sizeof(float), cudaHostAllocMapped));
   HSB_CUDA_C(cudaHostGetDevicePointer(&h->h_pin_dev, h->h_pin, 0));
@@ -579,7 +600,17 @@ int hsb_destroy(hsb_handle* h) {
                     &h->d_cloud, &h->d_cloud_off, &h->d_cloud_tf, &h->d_origo};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  for (int k = 0; k < 2; ++k) {
+    BatchSet& S = h->bset[k];
+    DevBuf* sb[] = {&S.hints, &S.in, &S.offsets, &S.poses, &S.cov, &S.origo, &S.tf};
+    for (DevBuf* b : sb)
+      if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 2; ++i)
+      if (S.done[i]) cudaEventDestroy(S.done[i]);
+  }
   if (h->d_dirty_all) cudaFree(h->d_dirty_all);
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_time[i]) cudaEventDestroy(h->ev_time[i]);
   for (int i = 0; i < 4; ++i)
     if (h->ev_sync[i]) cudaEventDestroy(h->ev_sync[i]);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -674,6 +705,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "prefetch")) h->tune_prefetch = value;
   else if (!strcmp(key, "trace")) h->tune_trace = value;
   else if (!strcmp(key, "pace")) h->tune_pace = value;
+  else if (!strcmp(key, "time_update")) h->tune_time_update = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }
@@ -750,71 +782,6 @@ int hsb_match_data(hsb_handle* h, const float hint[3], const float* pts, int n, 
   HSB_CUDA(h, cudaStreamSynchronize(st));
   memcpy(out_pose, h->h_pin + 4, 3 * sizeof(float));
   if (cov_inout && n > 0) memcpy(cov_inout, h->h_pin + 8, 9 * sizeof(float));
-  return HSB_OK;
-}
-
-int hsb_match_batch(hsb_handle* h, int B, const float* hints, const float* pts, const int* offsets, int n_shared,
-                    float* out_poses, float* out_cov) {
-  if (!h || B < 0 || !hints || !out_poses) return HSB_ERR_INVALID_ARG;
-  if (B == 0) return HSB_OK;
-  DeviceGuard guard(h->device);
-  size_t total = offsets ? (size_t)offsets[B] : (size_t)(n_shared > 0 ? n_shared : 0);
-  if (total > 0 && !pts) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
-  int s;
-  if ((s = ensure(h, h->d_hints, (size_t)B * 12)) != HSB_OK) return s;
-  if ((s = ensure(h, h->d_pts, total * 8 + 16)) != HSB_OK) return s;
-  if ((s = ensure(h, h->d_offsets, (size_t)(B + 1) * 4)) != HSB_OK) return s;
-  if ((s = ensure(h, h->d_poses, (size_t)B * 12)) != HSB_OK) return s;
-  if (out_cov && (s = ensure(h, h->d_cov, (size_t)B * 36)) != HSB_OK) return s;
-  float* d_hints = static_cast<float*>(h->d_hints.p);
-  float* d_pts = static_cast<float*>(h->d_pts.p);
-  int* d_off = static_cast<int*>(h->d_offsets.p);
-  float* d_poses = static_cast<float*>(h->d_poses.p);
-  float* d_cov = out_cov ? static_cast<float*>(h->d_cov.p) : nullptr;
-
-  int max_n = 0;
-  if (offsets) {
-    for (int b = 0; b < B; ++b) {
-      int n = offsets[b + 1] - offsets[b];
-      if (n < 0) return fail(h, HSB_ERR_INVALID_ARG, "offsets must be non-decreasing");
-      if (n > max_n) max_n = n;
-    }
-  } else {
-    max_n = n_shared > 0 ? n_shared : 0;
-  }
-
-  // Pipeline: the batch is cut into chunks; chunk c's host->device copy runs on copy stream c%2
-  // while chunk c-1 is being matched, and results stream back behind each kernel.
-  std::vector<int> bounds = pipeline_bounds(B, h->tune_chunk);
-  if (!offsets) bounds = std::vector<int>{0, B};  // shared scan: nothing big to overlap
-  ShapeScope shape_scope(h, B, bounds.size() - 1);
-  cudaStream_t s0 = h->copy_stream[0];
-  if (offsets) {
-    HSB_CUDA(h, cudaMemcpyAsync(d_off, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s0));
-  } else if (total > 0) {
-    HSB_CUDA(h, cudaMemcpyAsync(d_pts, pts, total * 8, cudaMemcpyHostToDevice, s0));
-  }
-  HSB_CUDA(h, cudaMemcpyAsync(d_hints, hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
-  HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
-  HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
-  for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
-    const int b0 = bounds[ci], b1 = bounds[ci + 1];
-    cudaStream_t st = h->copy_stream[ci & 1];
-    if (offsets) {
-      size_t p0 = (size_t)offsets[b0], p1 = (size_t)offsets[b1];
-      if (p1 > p0) HSB_CUDA(h, cudaMemcpyAsync(d_pts + 2 * p0, pts + 2 * p0, (p1 - p0) * 8, cudaMemcpyHostToDevice, st));
-    }
-    s = hsb_match_batch_device(h, b1 - b0, d_hints + 3 * (size_t)b0, d_pts, offsets ? d_off + b0 : nullptr, n_shared, max_n,
-                               d_poses + 3 * (size_t)b0, d_cov ? d_cov + 9 * (size_t)b0 : nullptr, st);
-    if (s != HSB_OK) return s;
-    HSB_CUDA(h, cudaMemcpyAsync(out_poses + 3 * (size_t)b0, d_poses + 3 * (size_t)b0, (size_t)(b1 - b0) * 12,
-                                cudaMemcpyDeviceToHost, st));
-    if (out_cov)
-      HSB_CUDA(h, cudaMemcpyAsync(out_cov + 9 * (size_t)b0, d_cov + 9 * (size_t)b0, (size_t)(b1 - b0) * 36,
-                                  cudaMemcpyDeviceToHost, st));
-  }
-  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[0]));
-  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[1]));
   return HSB_OK;
 }
 
@@ -920,47 +887,6 @@ int hsb_match_batch_ranges_device(hsb_handle* h, int B, const float* d_hints, co
   return launch_match(h, P, h->fmt.n_beams, (cudaStream_t)stream);
 }
 
-int hsb_match_batch_ranges(hsb_handle* h, int B, const float* hints, const float* ranges, float* out_poses, float* out_cov) {
-  if (!h || B < 0 || !hints || !ranges || !out_poses) return HSB_ERR_INVALID_ARG;
-  if (!h->fmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_scan_format has not been called");
-  if (B == 0) return HSB_OK;
-  DeviceGuard guard(h->device);
-  const size_t nb = (size_t)h->fmt.n_beams;
-  int s;
-  if ((s = ensure(h, h->d_hints, (size_t)B * 12)) != HSB_OK) return s;
-  if ((s = ensure(h, h->d_ranges, (size_t)B * nb * 4)) != HSB_OK) return s;
-  if ((s = ensure(h, h->d_poses, (size_t)B * 12)) != HSB_OK) return s;
-  if (out_cov && (s = ensure(h, h->d_cov, (size_t)B * 36)) != HSB_OK) return s;
-  float* d_hints = static_cast<float*>(h->d_hints.p);
-  float* d_ranges = static_cast<float*>(h->d_ranges.p);
-  float* d_poses = static_cast<float*>(h->d_poses.p);
-  float* d_cov = out_cov ? static_cast<float*>(h->d_cov.p) : nullptr;
-  // same copy/compute pipeline as hsb_match_batch
-  const std::vector<int> bounds = pipeline_bounds(B, h->tune_chunk);
-  ShapeScope shape_scope(h, B, bounds.size() - 1);
-  cudaStream_t s0 = h->copy_stream[0];
-  HSB_CUDA(h, cudaMemcpyAsync(d_hints, hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
-  HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
-  HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
-  for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
-    const int b0 = bounds[ci], b1 = bounds[ci + 1];
-    cudaStream_t st = h->copy_stream[ci & 1];
-    HSB_CUDA(h, cudaMemcpyAsync(d_ranges + (size_t)b0 * nb, ranges + (size_t)b0 * nb, (size_t)(b1 - b0) * nb * 4,
-                                cudaMemcpyHostToDevice, st));
-    s = hsb_match_batch_ranges_device(h, b1 - b0, d_hints + 3 * (size_t)b0, d_ranges + (size_t)b0 * nb,
-                                      d_poses + 3 * (size_t)b0, d_cov ? d_cov + 9 * (size_t)b0 : nullptr, st);
-    if (s != HSB_OK) return s;
-    HSB_CUDA(h, cudaMemcpyAsync(out_poses + 3 * (size_t)b0, d_poses + 3 * (size_t)b0, (size_t)(b1 - b0) * 12,
-                                cudaMemcpyDeviceToHost, st));
-    if (out_cov)
-      HSB_CUDA(h, cudaMemcpyAsync(out_cov + 9 * (size_t)b0, d_cov + 9 * (size_t)b0, (size_t)(b1 - b0) * 36,
-                                  cudaMemcpyDeviceToHost, st));
-  }
-  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[0]));
-  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[1]));
-  return HSB_OK;
-}
-
 // ---- point clouds (N2, the node's default input) ------------------------------------------------
 
 int hsb_set_cloud_format(hsb_handle* h, const hsb_cloud_format* fmt) {
@@ -1036,63 +962,274 @@ int hsb_match_batch_cloud_device(hsb_handle* h, int B, const float* d_hints, con
   return launch_match(h, P, max_points_per_scan, (cudaStream_t)stream);
 }
 
-int hsb_match_batch_cloud(hsb_handle* h, int B, const float* hints, const float* points_xyz, const int* offsets,
-                          const double* transforms, float* out_poses, float* out_cov, float* out_origo) {
-  if (!h || B < 0 || !hints || !offsets || !out_poses) return HSB_ERR_INVALID_ARG;
-  if (!h->cfmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_cloud_format has not been called");
-  if (B == 0) return HSB_OK;
-  DeviceGuard guard(h->device);
-  int max_n = 0;
-  for (int b = 0; b < B; ++b) {
-    const int n = offsets[b + 1] - offsets[b];
-    if (n < 0) return fail(h, HSB_ERR_INVALID_ARG, "offsets must be non-decreasing");
-    max_n = std::max(max_n, n);
-  }
-  const size_t total = (size_t)offsets[B] - (size_t)offsets[0];
-  if (total > 0 && !points_xyz) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+}  // extern "C"
+
+// ---- host-buffer batch calls: one pipelined implementation for the three input formats -----------
+// A call is cut into chunks (pipeline_bounds); chunk c's host->device copy runs on copy stream c%2 while chunk
+// c-1 is being matched, results stream back behind each kernel.  Two staging SETS of device buffers alternate
+// between calls, so that — with the submit / wait form — call k+1's first copies already travel while call k's
+// last chunk is still being matched: the steady state of a stream of batches is bound by the PCIe copy of the
+// inputs, not by copy + the exposed tail kernel.  The blocking entry points are submit + wait.
+namespace {
+
+enum { IN_ENDPOINTS = 0, IN_RANGES = 1, IN_CLOUD = 2 };
+struct HostBatch {
+  int kind = IN_ENDPOINTS;
+  int B = 0;
+  const float* hints = nullptr;
+  const float* in = nullptr;        // endpoints xy | ranges | cloud xyz
+  const int* offsets = nullptr;     // endpoints (NULL = shared scan) | cloud
+  int n_shared = 0;
+  const double* transforms = nullptr;
+  float* out_poses = nullptr;
+  float* out_cov = nullptr;
+  float* out_origo = nullptr;
+};
+
+int wait_set(hsb_handle* h, int s) {
+  BatchSet& S = h->bset[s];
+  if (!S.busy) return HSB_OK;
+  HSB_CUDA(h, cudaEventSynchronize(S.done[0]));
+  HSB_CUDA(h, cudaEventSynchronize(S.done[1]));
+  S.busy = false;
+  return HSB_OK;
+}
+
+int submit_host_batch(hsb_handle* h, const HostBatch& hb, int* ticket) {
+  const int B = hb.B;
+  const int si = h->next_set;
+  BatchSet& S = h->bset[si];
   int s;
-  if ((s = ensure(h, h->d_hints, (size_t)B * 12)) != HSB_OK) return s;
-  if ((s = ensure(h, h->d_cloud, ((size_t)offsets[B] + 1) * 12)) != HSB_OK) return s;
-  if ((s = ensure(h, h->d_cloud_off, (size_t)(B + 1) * 4)) != HSB_OK) return s;
-  if ((s = ensure(h, h->d_poses, (size_t)B * 12)) != HSB_OK) return s;
-  if (out_cov && (s = ensure(h, h->d_cov, (size_t)B * 36)) != HSB_OK) return s;
-  if (out_origo && (s = ensure(h, h->d_origo, (size_t)B * 8)) != HSB_OK) return s;
-  if (transforms && (s = ensure(h, h->d_cloud_tf, (size_t)B * 12 * sizeof(double))) != HSB_OK) return s;
-  float* d_hints = static_cast<float*>(h->d_hints.p);
-  float* d_cloud = static_cast<float*>(h->d_cloud.p);
-  int* d_off = static_cast<int*>(h->d_cloud_off.p);
-  float* d_poses = static_cast<float*>(h->d_poses.p);
-  float* d_cov = out_cov ? static_cast<float*>(h->d_cov.p) : nullptr;
-  float* d_origo = out_origo ? static_cast<float*>(h->d_origo.p) : nullptr;
-  double* d_tf = transforms ? static_cast<double*>(h->d_cloud_tf.p) : nullptr;
-  // same copy/compute pipeline as hsb_match_batch: chunk c's points travel while chunk c-1 is matched
-  const std::vector<int> bounds = pipeline_bounds(B, h->tune_chunk);
+  if ((s = wait_set(h, si)) != HSB_OK) return s;   // the set is reused: its previous call must have delivered
+  int max_n = 0;
+  size_t in_bytes = 0, unit = 8;
+  if (hb.kind == IN_RANGES) {
+    max_n = h->fmt.n_beams;
+    in_bytes = (size_t)B * (size_t)h->fmt.n_beams * 4;
+  } else {
+    unit = hb.kind == IN_CLOUD ? 12 : 8;
+    if (hb.offsets) {
+      for (int b = 0; b < B; ++b) {
+        const int n = hb.offsets[b + 1] - hb.offsets[b];
+        if (n < 0) return fail(h, HSB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+        max_n = std::max(max_n, n);
+      }
+      in_bytes = (size_t)hb.offsets[B] * unit;
+    } else {
+      max_n = hb.n_shared > 0 ? hb.n_shared : 0;
+      in_bytes = (size_t)max_n * unit;
+    }
+    if (in_bytes > 0 && !hb.in) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  }
+  if ((s = ensure(h, S.hints, (size_t)B * 12)) != HSB_OK) return s;
+  if ((s = ensure(h, S.in, in_bytes + 16)) != HSB_OK) return s;
+  if ((s = ensure(h, S.offsets, (size_t)(B + 1) * 4)) != HSB_OK) return s;
+  if ((s = ensure(h, S.poses, (size_t)B * 12)) != HSB_OK) return s;
+  if (hb.out_cov && (s = ensure(h, S.cov, (size_t)B * 36)) != HSB_OK) return s;
+  if (hb.out_origo && (s = ensure(h, S.origo, (size_t)B * 8)) != HSB_OK) return s;
+  if (hb.transforms && (s = ensure(h, S.tf, (size_t)B * 12 * sizeof(double))) != HSB_OK) return s;
+  float* d_hints = static_cast<float*>(S.hints.p);
+  char* d_in = static_cast<char*>(S.in.p);
+  int* d_off = static_cast<int*>(S.offsets.p);
+  float* d_poses = static_cast<float*>(S.poses.p);
+  float* d_cov = hb.out_cov ? static_cast<float*>(S.cov.p) : nullptr;
+  float* d_origo = hb.out_origo ? static_cast<float*>(S.origo.p) : nullptr;
+  double* d_tf = hb.transforms ? static_cast<double*>(S.tf.p) : nullptr;
+
+  std::vector<int> bounds = pipeline_bounds(B, h->tune_chunk);
+  const bool shared = hb.kind == IN_ENDPOINTS && !hb.offsets;
+  if (shared) bounds = std::vector<int>{0, B};   // one shared scan: nothing big to overlap
   ShapeScope shape_scope(h, B, bounds.size() - 1);
   cudaStream_t s0 = h->copy_stream[0];
-  HSB_CUDA(h, cudaMemcpyAsync(d_off, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s0));
-  HSB_CUDA(h, cudaMemcpyAsync(d_hints, hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
-  if (d_tf) HSB_CUDA(h, cudaMemcpyAsync(d_tf, transforms, (size_t)B * 12 * sizeof(double), cudaMemcpyHostToDevice, s0));
+  if (hb.offsets) HSB_CUDA(h, cudaMemcpyAsync(d_off, hb.offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s0));
+  if (shared && in_bytes > 0) HSB_CUDA(h, cudaMemcpyAsync(d_in, hb.in, in_bytes, cudaMemcpyHostToDevice, s0));
+  HSB_CUDA(h, cudaMemcpyAsync(d_hints, hb.hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
+  if (d_tf) HSB_CUDA(h, cudaMemcpyAsync(d_tf, hb.transforms, (size_t)B * 12 * sizeof(double), cudaMemcpyHostToDevice, s0));
   HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
   HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
   for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
     const int b0 = bounds[ci], b1 = bounds[ci + 1];
     cudaStream_t st = h->copy_stream[ci & 1];
-    const size_t p0 = (size_t)offsets[b0], p1 = (size_t)offsets[b1];
-    if (p1 > p0) HSB_CUDA(h, cudaMemcpyAsync(d_cloud + 3 * p0, points_xyz + 3 * p0, (p1 - p0) * 12, cudaMemcpyHostToDevice, st));
-    s = hsb_match_batch_cloud_device(h, b1 - b0, d_hints + 3 * (size_t)b0, d_cloud, d_off + b0, max_n, d_tf ? d_tf + 12 * (size_t)b0 : nullptr,
-                                     d_poses + 3 * (size_t)b0, d_cov ? d_cov + 9 * (size_t)b0 : nullptr,
-                                     d_origo ? d_origo + 2 * (size_t)b0 : nullptr, st);
+    if (!shared) {
+      size_t p0, p1;
+      if (hb.kind == IN_RANGES) {
+        p0 = (size_t)b0 * h->fmt.n_beams * 4;
+        p1 = (size_t)b1 * h->fmt.n_beams * 4;
+      } else {
+        p0 = (size_t)hb.offsets[b0] * unit;
+        p1 = (size_t)hb.offsets[b1] * unit;
+      }
+      if (p1 > p0)
+        HSB_CUDA(h, cudaMemcpyAsync(d_in + p0, reinterpret_cast<const char*>(hb.in) + p0, p1 - p0, cudaMemcpyHostToDevice, st));
+    }
+    float* o_pose = d_poses + 3 * (size_t)b0;
+    float* o_cov = d_cov ? d_cov + 9 * (size_t)b0 : nullptr;
+    if (hb.kind == IN_RANGES)
+      s = hsb_match_batch_ranges_device(h, b1 - b0, d_hints + 3 * (size_t)b0,
+                                        reinterpret_cast<const float*>(d_in) + (size_t)b0 * h->fmt.n_beams, o_pose, o_cov, st);
+    else if (hb.kind == IN_CLOUD)
+      s = hsb_match_batch_cloud_device(h, b1 - b0, d_hints + 3 * (size_t)b0, reinterpret_cast<const float*>(d_in), d_off + b0, max_n,
+                                       d_tf ? d_tf + 12 * (size_t)b0 : nullptr, o_pose, o_cov,
+                                       d_origo ? d_origo + 2 * (size_t)b0 : nullptr, st);
+    else
+      s = hsb_match_batch_device(h, b1 - b0, d_hints + 3 * (size_t)b0, reinterpret_cast<const float*>(d_in),
+                                 hb.offsets ? d_off + b0 : nullptr, hb.n_shared, max_n, o_pose, o_cov, st);
     if (s != HSB_OK) return s;
-    HSB_CUDA(h, cudaMemcpyAsync(out_poses + 3 * (size_t)b0, d_poses + 3 * (size_t)b0, (size_t)(b1 - b0) * 12, cudaMemcpyDeviceToHost, st));
-    if (out_cov)
-      HSB_CUDA(h, cudaMemcpyAsync(out_cov + 9 * (size_t)b0, d_cov + 9 * (size_t)b0, (size_t)(b1 - b0) * 36, cudaMemcpyDeviceToHost, st));
-    if (out_origo)
-      HSB_CUDA(h, cudaMemcpyAsync(out_origo + 2 * (size_t)b0, d_origo + 2 * (size_t)b0, (size_t)(b1 - b0) * 8, cudaMemcpyDeviceToHost, st));
+    HSB_CUDA(h, cudaMemcpyAsync(hb.out_poses + 3 * (size_t)b0, o_pose, (size_t)(b1 - b0) * 12, cudaMemcpyDeviceToHost, st));
+    if (hb.out_cov)
+      HSB_CUDA(h, cudaMemcpyAsync(hb.out_cov + 9 * (size_t)b0, o_cov, (size_t)(b1 - b0) * 36, cudaMemcpyDeviceToHost, st));
+    if (hb.out_origo)
+      HSB_CUDA(h, cudaMemcpyAsync(hb.out_origo + 2 * (size_t)b0, d_origo + 2 * (size_t)b0, (size_t)(b1 - b0) * 8,
+                                  cudaMemcpyDeviceToHost, st));
   }
-  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[0]));
-  HSB_CUDA(h, cudaStreamSynchronize(h->copy_stream[1]));
+  HSB_CUDA(h, cudaEventRecord(S.done[0], h->copy_stream[0]));
+  HSB_CUDA(h, cudaEventRecord(S.done[1], h->copy_stream[1]));
+  S.busy = true;
+  h->next_set = si ^ 1;
+  if (ticket) *ticket = si;
   return HSB_OK;
 }
+
+int run_host_batch(hsb_handle* h, const HostBatch& hb, int* ticket) {
+  int t = 0;
+  int s = submit_host_batch(h, hb, &t);
+  if (s != HSB_OK) return s;
+  if (ticket) {
+    *ticket = t;
+    return HSB_OK;
+  }
+  return wait_set(h, t);
+}
+
+int check_batch_args(hsb_handle* h, int B, const float* hints, float* out_poses) {
+  if (!h || B < 0 || !hints || !out_poses) return HSB_ERR_INVALID_ARG;
+  return HSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hsb_match_batch_submit(hsb_handle* h, int B, const float* hints, const float* pts, const int* offsets, int n_shared,
+                           float* out_poses, float* out_cov, int* ticket) {
+  int s = check_batch_args(h, B, hints, out_poses);
+  if (s != HSB_OK) return s;
+  if (B == 0) {
+    if (ticket) *ticket = -1;
+    return HSB_OK;
+  }
+  DeviceGuard guard(h->device);
+  HostBatch hb;
+  hb.kind = IN_ENDPOINTS;
+  hb.B = B;
+  hb.hints = hints;
+  hb.in = pts;
+  hb.offsets = offsets;
+  hb.n_shared = n_shared;
+  hb.out_poses = out_poses;
+  hb.out_cov = out_cov;
+  return run_host_batch(h, hb, ticket);
+}
+int hsb_match_batch(hsb_handle* h, int B, const float* hints, const float* pts, const int* offsets, int n_shared,
+                    float* out_poses, float* out_cov) {
+  return hsb_match_batch_submit(h, B, hints, pts, offsets, n_shared, out_poses, out_cov, nullptr);
+}
+
+int hsb_match_batch_ranges_submit(hsb_handle* h, int B, const float* hints, const float* ranges, float* out_poses,
+                                  float* out_cov, int* ticket) {
+  int s = check_batch_args(h, B, hints, out_poses);
+  if (s != HSB_OK) return s;
+  if (!ranges) return HSB_ERR_INVALID_ARG;
+  if (!h->fmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_scan_format has not been called");
+  if (B == 0) {
+    if (ticket) *ticket = -1;
+    return HSB_OK;
+  }
+  DeviceGuard guard(h->device);
+  HostBatch hb;
+  hb.kind = IN_RANGES;
+  hb.B = B;
+  hb.hints = hints;
+  hb.in = ranges;
+  hb.out_poses = out_poses;
+  hb.out_cov = out_cov;
+  return run_host_batch(h, hb, ticket);
+}
+int hsb_match_batch_ranges(hsb_handle* h, int B, const float* hints, const float* ranges, float* out_poses, float* out_cov) {
+  return hsb_match_batch_ranges_submit(h, B, hints, ranges, out_poses, out_cov, nullptr);
+}
+
+int hsb_match_batch_cloud_submit(hsb_handle* h, int B, const float* hints, const float* points_xyz, const int* offsets,
+                                 const double* transforms, float* out_poses, float* out_cov, float* out_origo, int* ticket) {
+  int s = check_batch_args(h, B, hints, out_poses);
+  if (s != HSB_OK) return s;
+  if (!offsets) return HSB_ERR_INVALID_ARG;
+  if (!h->cfmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_cloud_format has not been called");
+  if (B == 0) {
+    if (ticket) *ticket = -1;
+    return HSB_OK;
+  }
+  DeviceGuard guard(h->device);
+  HostBatch hb;
+  hb.kind = IN_CLOUD;
+  hb.B = B;
+  hb.hints = hints;
+  hb.in = points_xyz;
+  hb.offsets = offsets;
+  hb.transforms = transforms;
+  hb.out_poses = out_poses;
+  hb.out_cov = out_cov;
+  hb.out_origo = out_origo;
+  return run_host_batch(h, hb, ticket);
+}
+int hsb_match_batch_cloud(hsb_handle* h, int B, const float* hints, const float* points_xyz, const int* offsets,
+                          const double* transforms, float* out_poses, float* out_cov, float* out_origo) {
+  return hsb_match_batch_cloud_submit(h, B, hints, points_xyz, offsets, transforms, out_poses, out_cov, out_origo, nullptr);
+}
+
+int hsb_match_batch_wait(hsb_handle* h, int ticket) {
+  if (!h || ticket < -1 || ticket > 1) return HSB_ERR_INVALID_ARG;
+  if (ticket < 0) return HSB_OK;
+  DeviceGuard guard(h->device);
+  return wait_set(h, ticket);
+}
+
+int hsb_measure_h2d_gbs(hsb_handle* h, const void* host, size_t bytes, int reps, float* out_gbs) {
+  if (!h || !host || !bytes || reps < 1 || !out_gbs) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int s = ensure(h, h->d_occ, bytes);
+  if (s != HSB_OK) return s;
+  cudaStream_t st = h->stream;
+  HSB_CUDA(h, cudaMemcpyAsync(h->d_occ.p, host, bytes, cudaMemcpyHostToDevice, st));
+  HSB_CUDA(h, cudaEventRecord(h->ev_time[0], st));
+  for (int i = 0; i < reps; ++i) HSB_CUDA(h, cudaMemcpyAsync(h->d_occ.p, host, bytes, cudaMemcpyHostToDevice, st));
+  HSB_CUDA(h, cudaEventRecord(h->ev_time[1], st));
+  HSB_CUDA(h, cudaEventSynchronize(h->ev_time[1]));
+  float ms = 0.f;
+  HSB_CUDA(h, cudaEventElapsedTime(&ms, h->ev_time[0], h->ev_time[1]));
+  *out_gbs = (float)((double)bytes * reps / (ms * 1e-3) / 1e9);
+  return HSB_OK;
+}
+
+void* hsb_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+int hsb_free_pinned(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) {
+    cudaGetLastError();
+    return HSB_ERR_CUDA;
+  }
+  return HSB_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- map writing -------------------------------------------------------------------------------
 
@@ -1104,10 +1241,12 @@ static int run_update(hsb_handle* h, HsbUpdateParams& P, int max_n) {
   int blocks = (max_n * TEAM + 7) / 8;
   int cap = h->sm_count * 8;
   if (blocks > cap) blocks = cap;
+  if (h->tune_time_update) HSB_CUDA(h, cudaEventRecord(h->ev_time[0], st));
   hsb::update_mark_kernel<TEAM><<<dim3(blocks, P.levels), 256, 0, st>>>(P);
   int sweep = (h->sm_count * 8) / (P.levels > 0 ? P.levels : 1);
   if (sweep < 1) sweep = 1;
   hsb::update_apply_kernel<<<dim3(sweep, P.levels), 256, 0, st>>>(P);
+  if (h->tune_time_update) HSB_CUDA(h, cudaEventRecord(h->ev_time[1], st));
   h->launches += 2;
   HSB_CUDA(h, cudaGetLastError());
   return HSB_OK;

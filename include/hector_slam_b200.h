@@ -183,6 +183,33 @@ int hsb_match_batch_cloud_device(hsb_handle* h, int B, const float* d_hints_worl
                                  const int* d_offsets, int max_points_per_scan, const double* d_transforms,
                                  float* d_out_poses_world, float* d_out_cov, float* d_out_origo, void* stream);
 
+/* ---- streams of batches: submit / wait ---------------------------------------------------------*/
+/* The three host-buffer batch calls above are `submit` followed by `wait`.  Used separately they let a caller keep
+ * the PCIe link busy across calls: the handle owns TWO sets of device staging buffers that alternate between calls,
+ * so the copies of call k+1 travel while the last chunk of call k is still being matched.
+ *   submit  queues the copies and kernels of one batch and returns a ticket (it blocks only while the staging set it
+ *           is about to reuse — the one from two submits ago — has not delivered yet);
+ *   wait    returns when that batch's results are in its output buffers.
+ * Rules: at most two submits may be outstanding; input AND output buffers of a submit belong to the library until
+ * its wait returns (pinned host memory, e.g. hsb_alloc_pinned, is what makes the copies asynchronous — with pageable
+ * memory the calls still work but serialise); no map-writing call (hsb_update_by_scan, hsb_slam_update, hsb_reset,
+ * uploads) between a submit and its wait.  Results are identical to the blocking calls. */
+int hsb_match_batch_submit(hsb_handle* h, int B, const float* hints_world, const float* points_xy, const int* offsets,
+                           int n_shared, float* out_poses_world, float* out_cov, int* ticket);
+int hsb_match_batch_ranges_submit(hsb_handle* h, int B, const float* hints_world, const float* ranges,
+                                  float* out_poses_world, float* out_cov, int* ticket);
+int hsb_match_batch_cloud_submit(hsb_handle* h, int B, const float* hints_world, const float* points_xyz, const int* offsets,
+                                 const double* transforms, float* out_poses_world, float* out_cov, float* out_origo,
+                                 int* ticket);
+int hsb_match_batch_wait(hsb_handle* h, int ticket);
+/* Page-locked host memory for those buffers (cudaHostAlloc, allocated by the calling thread: bind the thread to the
+ * GPU's NUMA node first if the host has several).  NULL on failure. */
+void* hsb_alloc_pinned(size_t bytes);
+/* diagnostic: host->device copy rate of `bytes` from `host` (reps back-to-back copies timed with CUDA events) —
+ * bench.py reports it next to e2e so that a slow host path shows up as such */
+int hsb_measure_h2d_gbs(hsb_handle* h, const void* host, size_t bytes, int reps, float* out_gbs);
+int hsb_free_pinned(void* p);
+
 /* OccGridMapUtil::getCompleteHessianDerivs — map/OccGridMapUtil.h:64-104, one evaluation on one
  * level: `pose_map` and `points_level_xy` are in that level's cell units.  This is the finest
  * seam: the reference's own ScanMatcher can drive it one evaluation at a time. */
@@ -330,6 +357,9 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value);
  * endpoints of each scan staged in shared memory (0 = read through L1), grid size, resident CTAs per SM}.
  * Lets tests assert WHICH instantiation they compared with the oracle. */
 int hsb_get_last_launch_shape(const hsb_handle* h, int out[6]);
+/* Device time of the last map write's two kernels (mark + apply, CUDA events on the handle's stream), available when
+ * the tuning key "time_update" was set before the write — bench.py's K2 roofline. */
+int hsb_get_last_update_device_ms(hsb_handle* h, float* ms);
 /* Timeline of the last match launch when the tuning key "trace" is set: per scan 8 x uint64 =
  * {%globaltimer at start, after each level (coarsest first), at the end (slot 1 + levels), ..., %smid (slot 7)}.
  * Synchronises the device; returns the number of scans copied (<= max_scans) or a negative status. */

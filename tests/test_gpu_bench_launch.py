@@ -133,3 +133,43 @@ def test_e2e_launches_all_4096(workload):
     torch.cuda.synchronize()
     assert rep.last_launch_shape()["warps_per_scan"] == 1
     compare(d_p.cpu().numpy(), w, B, "ranges on the device, auto shape")
+
+
+def test_submit_wait_pipeline_equals_blocking_calls(workload):
+    """The submit / wait form (two staging sets, two calls in flight) returns the blocking calls' bits for all three
+    wire formats, with page-locked buffers from hsb_alloc_pinned."""
+    from hector_slam_b200 import capi, synth
+
+    w = workload
+    rep = w["rep"]
+    rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=0, prefetch=0)
+    rep.set_scan_format(**synth.SCAN_FORMAT)
+    B = 2048
+    hints, ranges = w["hints"][:B], w["ranges"][:B]
+    pts, offs = w["pts"][: w["offs"][B]], w["offs"][: B + 1]
+    want_r, cov_r = rep.match_batch_ranges(hints, ranges)
+    want_p, cov_p = rep.match_batch(hints, pts, offs)
+    hp = [capi.pinned_copy(hints), capi.pinned_copy(np.ascontiguousarray(hints[::-1]))]
+    rp = [capi.pinned_copy(ranges), capi.pinned_copy(np.ascontiguousarray(ranges[::-1]))]
+    op = [capi.PinnedArray((B, 3)), capi.PinnedArray((B, 3))]
+    oc = [capi.PinnedArray((B, 9)), capi.PinnedArray((B, 9))]
+    t0 = rep.match_batch_ranges_submit(hp[0].array, rp[0].array, op[0].array, oc[0].array)
+    t1 = rep.match_batch_ranges_submit(hp[1].array, rp[1].array, op[1].array, oc[1].array)   # both in flight
+    assert {t0, t1} == {0, 1}
+    rep.match_batch_wait(t0)
+    assert np.array_equal(op[0].array, want_r) and np.array_equal(oc[0].array.reshape(B, 3, 3), cov_r)
+    t2 = rep.match_batch_ranges_submit(hp[0].array, rp[0].array, op[0].array, oc[0].array)   # reuses set 0
+    rep.match_batch_wait(t1)
+    assert np.array_equal(op[1].array, want_r[::-1])          # a batch is a set of independent matches
+    rep.match_batch_wait(t2)
+    assert np.array_equal(op[0].array, want_r)
+    pp = capi.pinned_copy(pts)
+    t = rep.match_batch_submit(hp[0].array, pp.array, offs, op[1].array, oc[1].array)
+    rep.match_batch_wait(t)
+    assert np.array_equal(op[1].array, want_p) and np.array_equal(oc[1].array.reshape(B, 3, 3), cov_p)
+    rep.match_batch_wait(-1)                                   # ticket of an empty batch: no-op
+    gbs = rep.measure_h2d_gbs(rp[0].ptr, rp[0].array.nbytes)
+    report(f"hsb_alloc_pinned buffer of {rp[0].array.nbytes / 1e6:.1f} MB: {gbs:.1f} GB/s host->device")
+    assert gbs > 5.0
+    for a in hp + rp + op + oc + [pp]:
+        a.free()
