@@ -27,6 +27,10 @@ struct Level {
   float* prob = nullptr;
   uint32_t* stamp = nullptr;
   uint32_t stamp_base = 0;
+  int* scratch = nullptr;      // two slots of 8 ints for the two-phase writer (see HsbUpdateLevelDev)
+  int parity = 0;              // slot the NEXT map write of this level uses
+  unsigned* list = nullptr;    // cells marked by the scan being written
+  unsigned list_cap = 0;
   cudaArray_t arr = nullptr;
   cudaTextureObject_t tex = 0;
   cudaSurfaceObject_t surf = 0;
@@ -407,6 +411,8 @@ int destroy_level(hsb_handle* h, Level& L) {
   if (L.logodds) cudaFree(L.logodds);
   if (L.prob) cudaFree(L.prob);
   if (L.stamp) cudaFree(L.stamp);
+  if (L.scratch) cudaFree(L.scratch);
+  if (L.list) cudaFree(L.list);
   L = Level();
   (void)h;
   return HSB_OK;
@@ -556,6 +562,15 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
     HSB_CUDA_C(cudaMalloc(&L.prob, n * sizeof(float)));
     HSB_CUDA_C(cudaMalloc(&L.stamp, n * sizeof(uint32_t)));
     L.dirty = h->d_dirty_all + 8 * l;
+    HSB_CUDA_C(cudaMalloc(&L.scratch, 16 * sizeof(int)));
+    {
+      const int clean[16] = {0, INT_MAX, INT_MAX, -1, -1, 0, 0, 0, 0, INT_MAX, INT_MAX, -1, -1, 0, 0, 0};
+      HSB_CUDA_C(cudaMemcpy(L.scratch, clean, sizeof(clean), cudaMemcpyHostToDevice));
+    }
+    // a scan cannot mark more cells than the level has; 4 M entries (16 MB) cover any real scan, beyond that the
+    // apply phase falls back to sweeping the bounding box
+    L.list_cap = (unsigned)std::min<size_t>(n, (size_t)4 << 20);
+    HSB_CUDA_C(cudaMalloc(&L.list, (size_t)L.list_cap * sizeof(unsigned)));
     if (h->gather_mode == HSB_GATHER_TEX) {
       cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
       HSB_CUDA_C(cudaMallocArray(&L.arr, &desc, dx, dy, cudaArrayTextureGather | cudaArraySurfaceLoadStore));
@@ -736,8 +751,9 @@ int hsb_world_coords_pose(const hsb_handle* h, int level, const float map[3], fl
 
 // ---- matching ----------------------------------------------------------------------------------
 
-int hsb_match_batch_device(hsb_handle* h, int B, const float* d_hints, const float* d_pts, const int* d_offsets,
-                           int n_shared, int max_points_per_scan, float* d_out_poses, float* d_out_cov, void* stream) {
+static int match_device(hsb_handle* h, int B, const float* d_hints, const float* d_pts, const int* d_offsets, int n_shared,
+                        int max_points_per_scan, float* d_out_poses, float* d_out_cov, float* gate_state, const float* gate_in,
+                        float* gate_out_host, cudaStream_t stream) {
   if (!h || B < 0 || !d_hints || !d_out_poses) return HSB_ERR_INVALID_ARG;
   if (B == 0) return HSB_OK;
   if (!d_offsets && n_shared < 0) return fail(h, HSB_ERR_INVALID_ARG, "shared-scan mode needs n_shared >= 0");
@@ -752,9 +768,18 @@ int hsb_match_batch_device(hsb_handle* h, int B, const float* d_hints, const flo
   P.n_shared = d_offsets ? 0 : n_shared;
   P.out_poses = d_out_poses;
   P.out_cov = d_out_cov;
+  P.gate_state = gate_state;   // fused SLAM step only (B == 1)
+  P.gate_in = gate_in;
+  P.gate_out_host = gate_out_host;
   int max_n = d_offsets ? max_points_per_scan : n_shared;
   if (max_n < 0) max_n = 0;
-  return launch_match(h, P, max_n, (cudaStream_t)stream);
+  return launch_match(h, P, max_n, stream);
+}
+
+int hsb_match_batch_device(hsb_handle* h, int B, const float* d_hints, const float* d_pts, const int* d_offsets,
+                           int n_shared, int max_points_per_scan, float* d_out_poses, float* d_out_cov, void* stream) {
+  return match_device(h, B, d_hints, d_pts, d_offsets, n_shared, max_points_per_scan, d_out_poses, d_out_cov, nullptr, nullptr,
+                      nullptr, (cudaStream_t)stream);
 }
 
 int hsb_match_data(hsb_handle* h, const float hint[3], const float* pts, int n, const float origo[2], float out_pose[3],
@@ -1260,6 +1285,7 @@ static int next_stamp_base(hsb_handle* h, int level, uint32_t* base) {
   }
   *base = L.stamp_base;
   L.stamp_base += 4;
+  L.parity ^= 1;   // this write uses the slot fill_update_level just handed out; the next one the other
   return HSB_OK;
 }
 
@@ -1274,6 +1300,10 @@ static void fill_update_level(hsb_handle* h, int l, HsbUpdateLevelDev& d) {
   d.sy = L.sy;
   memcpy(d.mtw, L.mtw, sizeof(d.mtw));
   d.dirty = L.dirty;
+  d.scratch = L.scratch;
+  d.slot = L.parity;
+  d.list = L.list;
+  d.list_cap = L.list_cap;
 }
 
 // MapRepMultiMap::updateByScan (MapRepMultiMap.h:134-147) as launches on h->stream; level 0 reads `d_pts0`,
@@ -1362,13 +1392,15 @@ int hsb_slam_update(hsb_handle* h, const float hint[3], const float* pts, int n,
     h->last_n = n;
     h->last_origo[0] = origo ? origo[0] : 0.f;
     h->last_origo[1] = origo ? origo[1] : 0.f;
-    s = hsb_match_batch_device(h, 1, d_hdr, scan_points(pbuf), nullptr, n, n, d_s + 8, host_out ? h->h_pin_dev + 12 : d_s + 12, st);  // :78
+    // :78 match, and :83-89 the gate in the same kernel's epilogue (an empty scan still passes through it: pose = hint)
+    s = match_device(h, 1, d_hdr, scan_points(pbuf), nullptr, n, n, d_s + 8, host_out ? h->h_pin_dev + 12 : d_s + 12, d_gate,
+                     d_hdr + 3, host_out ? h->h_pin_dev + 8 : nullptr, st);
     if (s != HSB_OK) return s;
-    d_pose_in = d_s + 8;
+  } else {
+    hsb::slam_gate_kernel<<<1, 32, 0, st>>>(d_gate, d_hdr + 3, d_pose_in, d_s + 8, host_out ? h->h_pin_dev + 8 : nullptr);  // :80, :89
+    h->launches += 1;
+    HSB_CUDA(h, cudaGetLastError());
   }
-  hsb::slam_gate_kernel<<<1, 32, 0, st>>>(d_gate, d_hdr + 3, d_pose_in, d_s + 8, host_out ? h->h_pin_dev + 8 : nullptr);  // :83-89
-  h->launches += 1;
-  HSB_CUDA(h, cudaGetLastError());
   if ((s = enqueue_update_by_scan(h, reinterpret_cast<const float2*>(scan_points(pbuf)), n, origo, nullptr, d_s + 8, d_gate + 3)) != HSB_OK)  // :91
     return s;
   if (!host_out) HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 8, d_s + 8, 13 * sizeof(float), cudaMemcpyDeviceToHost, st));

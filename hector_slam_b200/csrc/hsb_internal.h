@@ -49,6 +49,10 @@ struct HsbMatchParams {
   float sqr_min_dist, sqr_max_dist, z_min, z_max;
   float* out_origo;         // B x 2 (may be null): dataContainer origo = laser position * scaleToMap
   float neg_zero;           // -0.0f, deliberately opaque to the compiler (see mul2_exact in match_kernel.cuh)
+  // fused SLAM step (B == 1): the gate of HectorSlamProcessor::update evaluated in the kernel's epilogue
+  float* gate_state;        // [0..2] lastMapUpdatePose, [3] flag out; nullptr = no gate
+  const float* gate_in;     // minDist, minAngle, force
+  float* gate_out_host;     // mapped host memory for pose + flag (may be nullptr)
   int pace_slack;           // > 0: groups of a CTA keep within this many evaluations of the slowest one (see match_kernel)
   int prefetch;             // != 0: L2 bulk prefetch of the part of a scan that is read from global memory
   // diagnostics (hsb_set_tuning "trace"): per scan 8 x u64 = {start, after coarsest level, ..., end (slot 1+levels), -, smid (slot 7)}
@@ -68,7 +72,14 @@ struct HsbUpdateLevelDev {
   float origo_x, origo_y;    // already in the units of `pts` before pt_scale
   uint32_t stamp_base;       // this scan's stamps: base+1 free, base+2 occupied
   int active;
-  int* dirty;                // {xmin, ymin, xmax, ymax} of cells written since the last reset (device)
+  int* dirty;                // two rectangles {xmin, ymin, xmax, ymax} of cells written since their last reset (device)
+  // per-scan scratch of the two-phase writer (device): two slots of 8 ints, {count, x0, y0, x1, y1, -, -, -}; the mark
+  // phase of a scan fills slot `slot` (number of cells it marked first + bounding box of start and end cells), the apply
+  // phase consumes it and clears the OTHER slot for the next scan
+  int* scratch;
+  int slot;
+  unsigned* list;            // cells marked by this scan, each exactly once (offsets into the level's planes)
+  unsigned list_cap;
 };
 
 struct HsbUpdateParams {

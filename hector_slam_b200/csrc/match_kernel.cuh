@@ -54,6 +54,39 @@ __device__ __forceinline__ float normalize_angle(float angle) {
   return a;
 }
 
+// util::poseDifferenceLargerThan (util/UtilFunctions.h:73-92): float norm, the angle wrapped with double pi.
+__device__ __forceinline__ bool pose_difference_larger_than(const float* p1, const float* p2, float dist_thresh,
+                                                            float ang_thresh) {
+  const float dx = __fsub_rn(p1[0], p2[0]), dy = __fsub_rn(p1[1], p2[1]);
+  if (__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) > dist_thresh) return true;
+  float a = __fsub_rn(p1[2], p2[2]);
+  const double pi = 3.14159265358979323846, two_pi = pi * 2.0;
+  if ((double)a > pi) a = (float)((double)a - two_pi);
+  else if ((double)a < -pi) a = (float)((double)a + two_pi);
+  return fabsf(a) > ang_thresh;
+}
+
+// HectorSlamProcessor::update's gate (slam_main/HectorSlamProcessor.h:83-95) evaluated on the device so that a
+// fused step needs no host round trip between match and map write.
+//   state: [0..2] lastMapUpdatePose, [3] out: 1.0f if the map is to be written by this step
+//   in   : [0] minDist, [1] minAngle, [2] force (map_without_matching)
+// pose_out (device) and pose_out_host (mapped host memory, may be null) receive the step's pose (the matched
+// pose, or the hint when matching is skipped) and, in [3], a copy of the flag.
+__device__ __forceinline__ void slam_gate(float* __restrict__ state, const float* __restrict__ in, float px, float py, float ppsi,
+                                          float* pose_out, float* pose_out_host) {
+  const float p[3] = {px, py, ppsi};
+  const bool upd = pose_difference_larger_than(p, state, in[0], in[1]) || in[2] != 0.0f;
+  if (upd) { state[0] = p[0]; state[1] = p[1]; state[2] = p[2]; }
+  const float flag = upd ? 1.0f : 0.0f;
+  state[3] = flag;
+  pose_out[0] = p[0]; pose_out[1] = p[1]; pose_out[2] = p[2];
+  pose_out[3] = flag;
+  if (pose_out_host) {   // mapped pinned host memory: the result needs no copy operation
+    pose_out_host[0] = p[0]; pose_out_host[1] = p[1]; pose_out_host[2] = p[2];
+    pose_out_host[3] = flag;
+  }
+}
+
 // Eigen's fixed-size 3x3 inverse times vector (ScanMatcher.h:205 `H.inverse() * dTr`): cyclic
 // cofactors, det from column 0, multiply by 1/det, no pivoting — restated with explicitly rounded
 // operations (no FMA contraction) because H is often ill-conditioned and the cancellation in the
@@ -809,10 +842,15 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
       P.trace[8 * (size_t)scan + 6] = warp_id();
       P.trace[8 * (size_t)scan + 7] = sm_id();
     }
-    if (t == 0) {
+    if (t == 0 && P.gate_state) {
+      // fused SLAM step (one scan): the map-update gate runs in the match kernel's epilogue — no separate launch
+      slam_gate(P.gate_state, P.gate_in, wx, wy, wpsi, P.out_poses, P.gate_out_host);
+    } else if (t == 0) {
       P.out_poses[3 * scan + 0] = wx;
       P.out_poses[3 * scan + 1] = wy;
       P.out_poses[3 * scan + 2] = wpsi;
+    }
+    if (t == 0) {
       if (P.out_cov) {  // covMatrix = H, ScanMatcher.h:184.  An empty scan leaves the caller's matrix
         // untouched in the reference (:68,189): hsb_match_data honours that on the host side, the
         // batch entry points document a zero matrix instead (`last` is still zero then).

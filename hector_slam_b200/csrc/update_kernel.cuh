@@ -25,6 +25,8 @@
 #ifndef HSB_UPDATE_KERNEL_CUH
 #define HSB_UPDATE_KERNEL_CUH
 
+#include <climits>
+
 #include "hsb_internal.h"
 #include "sincosf_glibc.h"
 
@@ -177,18 +179,6 @@ __global__ void __launch_bounds__(256)
 
 // ---- K2 -----------------------------------------------------------------------------------------
 
-// util::poseDifferenceLargerThan (util/UtilFunctions.h:73-92): float norm, the angle wrapped with double pi.
-__device__ __forceinline__ bool pose_difference_larger_than(const float* p1, const float* p2, float dist_thresh,
-                                                            float ang_thresh) {
-  const float dx = __fsub_rn(p1[0], p2[0]), dy = __fsub_rn(p1[1], p2[1]);
-  if (__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) > dist_thresh) return true;
-  float a = __fsub_rn(p1[2], p2[2]);
-  const double pi = 3.14159265358979323846, two_pi = pi * 2.0;
-  if ((double)a > pi) a = (float)((double)a - two_pi);
-  else if ((double)a < -pi) a = (float)((double)a + two_pi);
-  return fabsf(a) > ang_thresh;
-}
-
 // HectorSlamProcessor::update's gate (slam_main/HectorSlamProcessor.h:83-95) evaluated on the device so that a
 // fused step needs no host round trip between match and map write.
 //   state: [0..2] lastMapUpdatePose, [3] out: 1.0f if the map is to be written by this step
@@ -197,19 +187,7 @@ __device__ __forceinline__ bool pose_difference_larger_than(const float* p1, con
 // pose, or the hint when matching is skipped) and, in [3], a copy of the flag.
 __global__ void slam_gate_kernel(float* __restrict__ state, const float* __restrict__ in, const float* pose_in,
                                  float* pose_out, float* pose_out_host) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const float p[3] = {pose_in[0], pose_in[1], pose_in[2]};
-    const bool upd = pose_difference_larger_than(p, state, in[0], in[1]) || in[2] != 0.0f;
-    if (upd) { state[0] = p[0]; state[1] = p[1]; state[2] = p[2]; }
-    const float flag = upd ? 1.0f : 0.0f;
-    state[3] = flag;
-    pose_out[0] = p[0]; pose_out[1] = p[1]; pose_out[2] = p[2];
-    pose_out[3] = flag;
-    if (pose_out_host) {   // mapped pinned host memory: the result needs no copy operation
-      pose_out_host[0] = p[0]; pose_out_host[1] = p[1]; pose_out_host[2] = p[2];
-      pose_out_host[3] = flag;
-    }
-  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) slam_gate(state, in, pose_in[0], pose_in[1], pose_in[2], pose_out, pose_out_host);
 }
 
 // Per-level frame of one updateByScan call: the pose as Translation(x,y)*Rotation(psi) in this level's cells and
@@ -256,8 +234,23 @@ __device__ __forceinline__ bool beam_end(const HsbUpdateLevelDev& L, const BeamF
   return true;
 }
 
+// Warp-aggregated append: the active lanes of the warp that call this get consecutive slots of `list` with one atomic.
+__device__ __forceinline__ void list_append(unsigned* __restrict__ list, int* __restrict__ count, unsigned cap, unsigned value) {
+  const unsigned active = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(active) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(count, __popc(active));
+  base = __shfl_sync(active, base, leader);
+  const unsigned idx = (unsigned)base + (unsigned)__popc(active & ((1u << lane) - 1u));
+  if (idx < cap) list[idx] = value;
+}
+
 // MARK: a team of TEAM warps per beam; blockIdx.y = level.  Team lanes stride along the line, four cells per
-// lane in flight (the loop is bound by the L2 round trip of the stamp test, not by arithmetic).
+// lane in flight (the loop is bound by the L2 round trip of the stamp test, not by arithmetic).  The thread whose
+// atomicMax is the FIRST to stamp a cell in this scan also appends the cell to the scan's list, so the apply phase
+// visits exactly the touched cells (no sweep, one owner per cell by construction).  The bounding box of the start
+// cell and the beams' end cells goes to the scratch slot (dirty rectangles; fallback sweep if the list overflowed).
 template <int TEAM>
 __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant__ HsbUpdateParams P) {
   const HsbUpdateLevelDev& L = P.lv[blockIdx.y];
@@ -272,10 +265,13 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
   if (!f.ok) return;
   const unsigned start = (unsigned)f.y0 * (unsigned)L.sx + (unsigned)f.x0;
   const uint32_t free_s = L.stamp_base + 1u, occ_s = L.stamp_base + 2u;
+  int* slot = L.scratch + 8 * L.slot;
+  int bx0 = INT_MAX, by0 = INT_MAX, bx1 = -1, by1 = -1;
 
   for (int b = team0; b < L.n; b += team_stride) {
     int x1, y1;
     if (!beam_end(L, f, b, x1, y1)) continue;
+    bx0 = min(bx0, x1); by0 = min(by0, y1); bx1 = max(bx1, x1); by1 = max(by1, y1);
     const int dx = x1 - f.x0, dy = y1 - f.y0;
     const unsigned adx = (unsigned)abs(dx), ady = (unsigned)abs(dy);
     const int off_dx = dx > 0 ? 1 : -1;                         // util::sign, UtilFunctions.h:56-59
@@ -285,9 +281,20 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
     if (adx >= ady) { ada = adx; adb = ady; off_a = off_dx; off_b = off_dy; }   // :202-209
     else            { ada = ady; adb = adx; off_a = off_dy; off_b = off_dx; }
     const unsigned err0 = ada / 2u;
-    const bool narrow = ada < 46341u;   // err0 + i*adb < 2^31: 32-bit division
-    // cell i (0 <= i < ada; start included, end excluded, :245-259): the serial walk adds adb per step and
-    // carries when the error reaches ada, so after i steps it has carried floor((err0 + i*adb) / ada) times.
+    // cell i (0 <= i < ada; start included, end excluded, :245-259): the serial walk adds adb per step and carries when
+    // the error reaches ada, so after i steps it has carried q(i) = floor((err0 + i*adb) / ada) times.  A lane visits
+    // i = tlane, tlane + TL, ...: q and the remainder r are advanced by the constant step (TL*adb = qT*ada + rT) —
+    // two divisions per lane and beam instead of one per cell.
+    unsigned q, r, qT, rT;
+    if (ada < 32768u) {   // err0 + i*adb and TL*adb fit 32 bits
+      const unsigned n0 = err0 + tlane * adb, nT = (unsigned)TL * adb;
+      q = n0 / ada; r = n0 - q * ada;
+      qT = nT / ada; rT = nT - qT * ada;
+    } else {
+      const unsigned long long n0 = (unsigned long long)err0 + (unsigned long long)tlane * adb, nT = (unsigned long long)TL * adb;
+      q = (unsigned)(n0 / ada); r = (unsigned)(n0 - (unsigned long long)q * ada);
+      qT = (unsigned)(nT / ada); rT = (unsigned)(nT - (unsigned long long)qT * ada);
+    }
     for (unsigned i0 = tlane; i0 < ada; i0 += U * TL) {
       unsigned off[U];
       uint32_t v[U];
@@ -296,24 +303,44 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
         const unsigned i = i0 + (unsigned)(k * TL);
         v[k] = 0xffffffffu;
         if (i < ada) {
-          const unsigned carries = narrow ? (err0 + i * adb) / ada
-                                          : (unsigned)(((unsigned long long)err0 + (unsigned long long)i * adb) / ada);
-          off[k] = start + (unsigned)((int)i * off_a) + (unsigned)((int)carries * off_b);
+          off[k] = start + (unsigned)((int)i * off_a) + (unsigned)((int)q * off_b);
           v[k] = __ldcg(L.stamp + off[k]);
         }
+        q += qT;
+        r += rT;
+        if (r >= ada) { r -= ada; ++q; }
       }
 #pragma unroll
       for (int k = 0; k < U; ++k)
-        if (v[k] < free_s) atomicMax(L.stamp + off[k], free_s);   // bresenhamCellFree :216-224
+        if (v[k] < free_s) {                                       // bresenhamCellFree :216-224
+          if (atomicMax(L.stamp + off[k], free_s) < free_s) list_append(L.list, slot, L.list_cap, off[k]);
+        }
     }
-    if (tlane == 0) atomicMax(L.stamp + (unsigned)y1 * (unsigned)L.sx + (unsigned)x1, occ_s);   // bresenhamCellOcc :226-241, :211-212
+    if (tlane == 0) {                                              // bresenhamCellOcc :226-241, :211-212
+      const unsigned eoff = (unsigned)y1 * (unsigned)L.sx + (unsigned)x1;
+      if (atomicMax(L.stamp + eoff, occ_s) < free_s) list_append(L.list, slot, L.list_cap, eoff);
+    }
+  }
+  // bounding box of this warp's beams (+ the common start cell) -> scratch slot, 4 atomics per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+    by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+    bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+    by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+  }
+  if ((threadIdx.x & 31) == 0 && bx1 >= 0) {
+    atomicMin(slot + 1, min(bx0, f.x0));
+    atomicMin(slot + 2, min(by0, f.y0));
+    atomicMax(slot + 3, max(bx1, f.x0));
+    atomicMax(slot + 4, max(by1, f.y0));
   }
 }
 
-// APPLY: every cell marked by this scan lies in the bounding box of the start cell and the end cells, so the
-// apply phase is a coalesced sweep of that box over the stamp plane — no atomics, one owner per cell by
-// construction.  Each CTA recomputes the box from the beams (1081 transforms, cheaper than a grid-wide
-// reduction plus a host round trip); CTA 0 also folds it into the level's dirty rectangle (tile replication).
+// APPLY: every cell the scan marked is in its list exactly once: a grid-stride pass over the list applies the
+// log-odds update and rewrites the probability (and the texture twin) — no atomics, one owner per cell, deterministic
+// values whatever the list order.  Should the list have overflowed (more cells than its capacity), the pass falls back
+// to a sweep over the bounding box, testing every stamp.
 __device__ __forceinline__ void apply_cell(const HsbUpdateLevelDev& L, unsigned off, uint32_t v, float lf, float lo) {
   const uint32_t d = v - (L.stamp_base + 1u);
   if (d < 2u) {
@@ -336,33 +363,16 @@ __device__ __forceinline__ void apply_cell(const HsbUpdateLevelDev& L, unsigned 
 __global__ void __launch_bounds__(256) update_apply_kernel(const __grid_constant__ HsbUpdateParams P) {
   const HsbUpdateLevelDev& L = P.lv[blockIdx.y];
   if (!L.active) return;
+  const int* cur = L.scratch + 8 * L.slot;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {   // the other slot is the next scan's: clear it (nobody reads it now)
+    int* nxt = L.scratch + 8 * (L.slot ^ 1);
+    nxt[0] = 0;
+    nxt[1] = INT_MAX; nxt[2] = INT_MAX; nxt[3] = -1; nxt[4] = -1;
+  }
   if (P.gate_flag && *P.gate_flag == 0.0f) return;
-  const BeamFrame f = beam_frame(P, L);
-  if (!f.ok) return;
-  __shared__ int red[4][8];
-  int bx0 = f.x0, by0 = f.y0, bx1 = f.x0, by1 = f.y0, any = 0;
-  for (int b = threadIdx.x; b < L.n; b += blockDim.x) {
-    int x1, y1;
-    if (beam_end(L, f, b, x1, y1)) {
-      bx0 = min(bx0, x1); by0 = min(by0, y1); bx1 = max(bx1, x1); by1 = max(by1, y1);
-      any = 1;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-    by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-    bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-    by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-  }
-  any = __syncthreads_or(any);
-  if (!any) return;
-  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if ((threadIdx.x & 31) == 0) { red[0][w] = bx0; red[1][w] = by0; red[2][w] = bx1; red[3][w] = by1; }
-  __syncthreads();
-  for (int k = 0; k < nw; ++k) {
-    bx0 = min(bx0, red[0][k]); by0 = min(by0, red[1][k]); bx1 = max(bx1, red[2][k]); by1 = max(by1, red[3][k]);
-  }
+  const int bx0 = cur[1], by0 = cur[2], bx1 = cur[3], by1 = cur[4];
+  if (bx1 < bx0) return;                       // nothing was marked (pose outside the map, every beam dropped)
+  const unsigned count = (unsigned)cur[0];
   if (blockIdx.x == 0 && threadIdx.x == 0 && L.dirty) {   // both rectangles: replication [0..3] and host mirror [4..7]
     atomicMin(L.dirty + 0, bx0); atomicMin(L.dirty + 4, bx0);
     atomicMin(L.dirty + 1, by0); atomicMin(L.dirty + 5, by0);
@@ -371,39 +381,29 @@ __global__ void __launch_bounds__(256) update_apply_kernel(const __grid_constant
   }
   const float lf = P.log_odds_free, lo = P.log_odds_occ;
   const unsigned nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned rows = (unsigned)(by1 - by0 + 1);
   constexpr int U = 4;
-  if ((L.sx & 3) == 0) {   // rows are 16-byte aligned: four cells per load
-    const unsigned xa = (unsigned)bx0 & ~3u;
-    const unsigned w4 = (((unsigned)bx1 - xa) >> 2) + 1u;
-    const unsigned total = w4 * rows;
-    for (unsigned base = tid; base < total; base += U * nthreads) {
+  if (count <= L.list_cap) {
+    for (unsigned base = tid; base < count; base += U * nthreads) {
       unsigned off[U];
-      uint4 v[U];
+      uint32_t v[U];
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        const unsigned idx = base + (unsigned)k * nthreads;
-        v[k] = make_uint4(L.stamp_base, L.stamp_base, L.stamp_base, L.stamp_base);
-        if (idx < total) {
-          const unsigned r = idx / w4, c = idx - r * w4;
-          off[k] = ((unsigned)by0 + r) * (unsigned)L.sx + xa + 4u * c;
-          v[k] = __ldcg(reinterpret_cast<const uint4*>(L.stamp + off[k]));
+        const unsigned i = base + (unsigned)k * nthreads;
+        v[k] = L.stamp_base;
+        if (i < count) {
+          off[k] = __ldcg(L.list + i);
+          v[k] = __ldcg(L.stamp + off[k]);
         }
       }
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        apply_cell(L, off[k] + 0u, v[k].x, lf, lo);
-        apply_cell(L, off[k] + 1u, v[k].y, lf, lo);
-        apply_cell(L, off[k] + 2u, v[k].z, lf, lo);
-        apply_cell(L, off[k] + 3u, v[k].w, lf, lo);
-      }
+      for (int k = 0; k < U; ++k) apply_cell(L, off[k], v[k], lf, lo);
     }
   } else {
-    const unsigned wd = (unsigned)(bx1 - bx0 + 1);
+    const unsigned wd = (unsigned)(bx1 - bx0 + 1), rows = (unsigned)(by1 - by0 + 1);
     const unsigned total = wd * rows;
     for (unsigned idx = tid; idx < total; idx += nthreads) {
-      const unsigned r = idx / wd, c = idx - r * wd;
-      const unsigned off = ((unsigned)by0 + r) * (unsigned)L.sx + (unsigned)bx0 + c;
+      const unsigned rr = idx / wd, c = idx - rr * wd;
+      const unsigned off = ((unsigned)by0 + rr) * (unsigned)L.sx + (unsigned)bx0 + c;
       apply_cell(L, off, __ldcg(L.stamp + off), lf, lo);
     }
   }

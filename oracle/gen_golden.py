@@ -228,9 +228,83 @@ def main(kind="reference"):
     planes_sparse(os_, "final", out)
     np.savez_compressed(os.path.join(OUT, "slam3.npz"), **out)
     os_.close()
+    gen_next(kind)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def gen_next(kind="reference"):
+    """next.npz — the "next" rows of SURVEY.md §8f, from the compiled reference: the node's point-cloud converter
+    (HectorMappingRos.cpp:509-542, source text compiled by oracle/ros_conv_driver.cpp), the sigma-point covariance
+    (OccGridMapUtil.h:106-187) and hector_map_tools' ray cast / getDist (HectorMapTools.h:133-237, header compiled by
+    oracle/maptools_driver.cpp) on the match3 map."""
+    from oracle import pyoracle
+
+    g = np.load(os.path.join(OUT, "match3.npz"))
+    out = {}
+    # point clouds
+    rng = np.random.default_rng(77)
+    fmt = synth.CLOUD_FORMAT
+    world = synth.World(1, seed=1234)
+    clouds, Ts, kept, origos = [], [], [], []
+    for k in range(6):
+        T = synth.laser_transform(xyz=rng.uniform(-0.3, 0.3, 3), rpy=rng.uniform(-0.06, 0.06, 3))
+        pose = world.sample_free_poses(1, rng)[0]
+        cloud = synth.ranges_to_cloud(world.cast(pose) + rng.normal(0, 0.01, synth.N_BEAMS))
+        cloud[::11, 2] = rng.uniform(-1.6, 1.6, cloud[::11].shape[0])         # some outside the z window
+        cloud[5] = (-0.5, 0.3, 0.0)
+        cloud[6] = (0.3, 0.2, 0.0)
+        pts, og = pyoracle.cloud_to_points(cloud, T, fmt["sqr_laser_min_dist"], fmt["sqr_laser_max_dist"],
+                                           fmt["laser_z_min_value"], fmt["laser_z_max_value"], 20.0, kind=kind)
+        clouds.append(cloud)
+        Ts.append(T)
+        kept.append(pts)
+        origos.append(og)
+    out["cloud_offsets"] = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int32)
+    out["cloud_xyz"] = np.concatenate(clouds).astype(np.float32)
+    out["cloud_T"] = np.asarray(Ts, np.float64)
+    out["cloud_kept_offsets"] = np.concatenate([[0], np.cumsum([c.shape[0] for c in kept])]).astype(np.int32)
+    out["cloud_kept"] = np.concatenate(kept).astype(np.float32)
+    out["cloud_origo"] = np.asarray(origos, np.float32)
+    # covariance + map tools on the match3 map
+    size = int(g["size"])
+    orc = Oracle(kind, float(g["res"]), size, 3)
+    for l in range(3):
+        p = np.zeros((size >> l) ** 2, np.float32)
+        p[g[f"map_idx{l}"]] = g[f"map_val{l}"]
+        orc.set_logodds(l, p.reshape(size >> l, size >> l))
+    cm, cw = [], []
+    for l in range(3):
+        for k in range(K):
+            a, b = orc.covariance_for_pose(l, orc.map_coords_pose(l, g["ref_poses"][k]),
+                                           (g["scans"][k] * np.float32(2.0 ** -l)).astype(np.float32))
+            cm.append(a)
+            cw.append(b)
+    out["cov_map"] = np.asarray(cm, np.float32).reshape(3, K, 3, 3)
+    out["cov_world"] = np.asarray(cw, np.float32).reshape(3, K, 3, 3)
+    port = Oracle("port", float(g["res"]), size, 3)   # only for the level geometry (map origin)
+    lo = orc.get_logodds(0)
+    occ = np.where(lo < 0, 0, np.where(lo > 0, 100, -1)).astype(np.int8)
+    origin = port.map_origin(0)
+    mt = pyoracle.RefMapTools(occ, float(g["res"]), origin)
+    B = 400
+    begin = rng.integers(int(0.3 * size), int(0.7 * size), (B, 2)).astype(np.int32)
+    end = rng.integers(-5, size + 5, (B, 2)).astype(np.int32)
+    bw = rng.uniform(-7, 7, (B, 2)).astype(np.float32)
+    ew = rng.uniform(-14, 14, (B, 2)).astype(np.float32)
+    rc = [mt.raycast(begin[i], end[i]) for i in range(B)]
+    gd = [mt.get_dist(bw[i], ew[i]) for i in range(B)]
+    out.update(ray_begin=begin, ray_end=end, ray_dist=np.float32([r[0] for r in rc]), ray_hit=np.int32([r[1] for r in rc]),
+               gd_begin=bw, gd_end=ew, gd_dist=np.float32([r[0] for r in gd]), gd_hit=np.float32([r[1] for r in gd]),
+               gd_found=np.int8([r[2] for r in gd]), map_origin=origin)
+    mt.close()
+    orc.close()
+    port.close()
+    np.savez_compressed(os.path.join(OUT, "next.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "next":
+        gen_next()
+    else:
+        main()

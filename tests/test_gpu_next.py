@@ -273,3 +273,34 @@ def test_gate_state_survives_mixing_fused_and_host_driven_steps(hsb_lib):
     _, _, upd3 = rep.slam_update(rep.last_map_update_pose(), g["scans"][1])
     assert not upd3
     rep.close()
+
+
+def test_next_rows_against_reference_goldens(hsb_lib):
+    """The CUDA path against tests/golden/next.npz — vectors produced by the compiled reference itself (node converter
+    source, OccGridMapUtil.h, HectorMapTools.h): conversion, ray cast and getDist bit-exact, covariance to 2e-5."""
+    from hector_slam_b200 import capi, synth
+
+    g, m = load_golden("next.npz"), load_golden("match3.npz")
+    size = int(m["size"])
+    rep = capi.MapRepB200(float(m["res"]), size, levels=3)
+    for l, p in enumerate(golden_planes(m)):
+        rep.upload_level(l, p)
+    co, ko = g["cloud_offsets"], g["cloud_kept_offsets"]
+    for k in range(len(co) - 1):
+        rep.set_cloud_format(g["cloud_T"][k], **synth.CLOUD_FORMAT)
+        pts, og = rep.cloud_to_points(g["cloud_xyz"][co[k]:co[k + 1]])
+        assert np.array_equal(pts, g["cloud_kept"][ko[k]:ko[k + 1]]) and np.array_equal(og, g["cloud_origo"][k])
+    K = m["scans"].shape[0]
+    pts = m["scans"].reshape(-1, 2)
+    offs = (np.arange(K + 1) * m["scans"].shape[1]).astype(np.int32)
+    for l in range(3):
+        cm, cw = rep.covariance_batch(l, m["ref_poses"], pts, offs)
+        assert np.abs(cm - g["cov_map"][l]).max(axis=(1, 2)).max() <= 2e-5 * np.abs(g["cov_map"][l]).max()
+        assert (np.abs(cw - g["cov_world"][l]).max(axis=(1, 2)) <= 2e-5 * np.abs(g["cov_world"][l]).max(axis=(1, 2))).all()
+    assert np.array_equal(rep.map_origin(0), g["map_origin"])
+    dist, hit = rep.raycast_batch(0, g["ray_begin"], g["ray_end"])
+    assert np.array_equal(dist, g["ray_dist"]) and np.array_equal(hit, g["ray_hit"])
+    dist, hw, found = rep.get_dist_batch(0, g["gd_begin"], g["gd_end"])
+    assert np.array_equal(dist, g["gd_dist"]) and np.array_equal(found, g["gd_found"].astype(bool))
+    assert np.array_equal(hw[found], g["gd_hit"][found])
+    rep.close()

@@ -246,3 +246,31 @@ def test_covariance_and_map_tools_port_equals_reference(pyoracle, oracle_kinds):
         mt.close()
     port.close()
     ref.close()
+
+
+def test_next_rows_goldens_bit_exact(pyoracle):
+    """tests/golden/next.npz (generated from the compiled reference: node converter source text, OccGridMapUtil.h,
+    HectorMapTools.h): the C port reproduces every vector bit for bit on any machine."""
+    from hector_slam_b200 import synth
+
+    g, m = load_golden("next.npz"), load_golden("match3.npz")
+    fmt = synth.CLOUD_FORMAT
+    co, ko = g["cloud_offsets"], g["cloud_kept_offsets"]
+    for k in range(len(co) - 1):
+        pts, og = pyoracle.cloud_to_points(g["cloud_xyz"][co[k]:co[k + 1]], g["cloud_T"][k], fmt["sqr_laser_min_dist"],
+                                           fmt["sqr_laser_max_dist"], fmt["laser_z_min_value"], fmt["laser_z_max_value"], 20.0)
+        assert np.array_equal(pts, g["cloud_kept"][ko[k]:ko[k + 1]]) and np.array_equal(og, g["cloud_origo"][k])
+    o = make(pyoracle, "port", m)
+    set_planes(o, golden_planes(m))
+    for l in range(3):
+        for k in range(m["scans"].shape[0]):
+            a, b = o.covariance_for_pose(l, o.map_coords_pose(l, m["ref_poses"][k]),
+                                         (m["scans"][k] * np.float32(2.0 ** -l)).astype(np.float32))
+            assert np.array_equal(a, g["cov_map"][l, k]) and np.array_equal(b, g["cov_world"][l, k])
+    assert np.array_equal(o.map_origin(0), g["map_origin"])
+    for i in range(len(g["ray_dist"])):
+        d, h = o.raycast(0, g["ray_begin"][i], g["ray_end"][i])
+        assert d == g["ray_dist"][i] and h == tuple(g["ray_hit"][i])
+        d, hw, f = o.get_dist(0, g["gd_begin"][i], g["gd_end"][i])
+        assert np.float32(d) == g["gd_dist"][i] and f == bool(g["gd_found"][i]) and np.array_equal(hw, g["gd_hit"][i])
+    o.close()
