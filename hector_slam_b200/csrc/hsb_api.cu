@@ -94,7 +94,7 @@ struct hsb_handle {
   DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
   float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1;
   DevBuf d_trace;
   int trace_scans = 0;
   int last_shape[6] = {0, 0, 0, 0, 0, 0};  // W, G, U, staged points per scan (0 = none), grid, resident CTAs / SM
@@ -721,6 +721,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "trace")) h->tune_trace = value;
   else if (!strcmp(key, "pace")) h->tune_pace = value;
   else if (!strcmp(key, "time_update")) h->tune_time_update = value;
+  else if (!strcmp(key, "pdl")) h->tune_pdl = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }
@@ -1267,10 +1268,27 @@ static int run_update(hsb_handle* h, HsbUpdateParams& P, int max_n) {
   int cap = h->sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (h->tune_time_update) HSB_CUDA(h, cudaEventRecord(h->ev_time[0], st));
-  hsb::update_mark_kernel<TEAM><<<dim3(blocks, P.levels), 256, 0, st>>>(P);
   int sweep = (h->sm_count * 8) / (P.levels > 0 ? P.levels : 1);
   if (sweep < 1) sweep = 1;
-  hsb::update_apply_kernel<<<dim3(sweep, P.levels), 256, 0, st>>>(P);
+  if (h->tune_pdl) {
+    // programmatic dependent launch: see pdl_wait() in update_kernel.cuh
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3(blocks, P.levels);
+    HSB_CUDA(h, cudaLaunchKernelEx(&cfg, hsb::update_mark_kernel<TEAM>, P));
+    cfg.gridDim = dim3(sweep, P.levels);
+    HSB_CUDA(h, cudaLaunchKernelEx(&cfg, hsb::update_apply_kernel, P));
+  } else {
+    hsb::update_mark_kernel<TEAM><<<dim3(blocks, P.levels), 256, 0, st>>>(P);
+    hsb::update_apply_kernel<<<dim3(sweep, P.levels), 256, 0, st>>>(P);
+  }
   if (h->tune_time_update) HSB_CUDA(h, cudaEventRecord(h->ev_time[1], st));
   h->launches += 2;
   HSB_CUDA(h, cudaGetLastError());

@@ -155,11 +155,23 @@ struct LevelRegs {
   const float* prob;
   int sx;
 };
+// A texture instruction wants its (bindless) handle in a UNIFORM register.  The handle of the current level is read
+// from the kernel parameters with a run-time level index, which ptxas does not recognise as warp-uniform: it then wraps
+// EVERY gather in a "waterfall" loop (R2UR / PLOP3 / BRA.U.ANY — 8 extra instructions per TLD4, ~15 % of the whole
+// kernel, measured in the round-1 SASS).  A warp reduction (redux.sync -> REDUX, whose result lands in a uniform
+// register) of the — identical — per-lane copies makes the uniformity visible: the TLD4s take the handle from UR
+// directly.  Must be called with all 32 lanes converged (every caller does, once per level).
+__device__ __forceinline__ cudaTextureObject_t uniform_handle(cudaTextureObject_t t) {
+  const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(t & 0xffffffffull));
+  const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(t >> 32));
+  return ((cudaTextureObject_t)hi << 32) | (cudaTextureObject_t)lo;
+}
+
 __device__ __forceinline__ LevelRegs level_regs(const HsbLevelDev& L) {
   LevelRegs r;
   r.lim_x = L.lim_x;
   r.lim_y = L.lim_y;
-  r.tex = L.tex;
+  r.tex = uniform_handle(L.tex);
   r.prob = L.prob;
   r.sx = L.sx;
   return r;
@@ -652,6 +664,9 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
   uint64_t* mbar = mbars + g;
   int* warp_cnt = cnt_all + g * 32;
 
+  // fused SLAM step: let the map writer's CTAs (launched with programmatic stream serialisation, update_kernel.cuh)
+  // become resident on the idle SMs while this single-scan match runs; they wait for this grid's completion
+  if (P.gate_state) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (t == 0) mbar_init(mbar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   // Pacing (G > 1, P.pace_slack > 0).  Measured with the per-scan timeline (profiles/r02_k1_timeline.md): the warps of

@@ -1,0 +1,11 @@
+#!/bin/bash
+# One GPU-box session: everything this round needs measured, most important first, each step with its own timeout and log
+# under gpurun_out/ (merged back by gpurun).  Usage (from the repo root on the box): bash scripts/gpu_session.sh <tag>
+tag=${1:-s}
+out=gpurun_out
+mkdir -p $out
+export PYTHONUNBUFFERED=1
+echo "== pytest (full gpu suite)"; timeout 900 python -m pytest tests -m gpu -q -x > $out/${tag}_pytest.log 2>&1; tail -3 $out/${tag}_pytest.log
+echo "== k1 probe"; timeout 300 python scripts/k1_probe.py 4096 > $out/${tag}_k1_probe.log 2>&1; head -40 $out/${tag}_k1_probe.log
+echo "== bench N=1"; timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 600 $out/${tag}_bench.err; head -c 1500 $out/${tag}_bench.json
+echo "== reference arm"; timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err

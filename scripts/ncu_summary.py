@@ -38,6 +38,8 @@ WANT = [
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput %"),
     ("lts__t_sector_hit_rate.pct", "L2 sector hit rate %"),
     ("lts__t_bytes.sum", "L2 bytes"),
+    ("lts__t_sectors.sum", "L2 sectors"),
+    ("l1tex__t_bytes.sum", "L1TEX bytes"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
     ("dram__bytes_read.sum", "dram__bytes_read.sum"),
     ("dram__bytes_write.sum", "dram__bytes_write.sum"),
@@ -90,7 +92,20 @@ def main():
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
 
         r = data[-1]
+
+        def opt(key, scale=1.0):
+            try:
+                return val(key, r) * scale
+            except (KeyError, ValueError):
+                return None
+
         out = {"dram_read_bytes": val("dram__bytes_read.sum", r), "dram_write_bytes": val("dram__bytes_write.sum", r),
+               "lts_bytes": opt("lts__t_bytes.sum"), "l1tex_bytes": opt("l1tex__t_bytes.sum"),
+               "l2_hit_rate": opt("lts__t_sector_hit_rate.pct", 0.01), "l1_hit_rate": opt("l1tex__t_sector_hit_rate.pct", 0.01),
+               "tex_writeback_frac": opt("l1tex__tex_writeback_active.avg.pct_of_peak_sustained_elapsed", 0.01),
+               "issue_frac": opt("smsp__issue_active.avg.pct_of_peak_sustained_active", 0.01),
+               "achieved_occupancy": opt("sm__warps_active.avg.pct_of_peak_sustained_active", 0.01),
+               "duration_us_under_ncu": opt("gpu__time_duration.sum"),
                "kernel": r[idx["Kernel Name"]], "source": "ncu --set full capture " + rep.split("/")[-1]}
         open(sys.argv[sys.argv.index("--traffic") + 1], "w").write(json.dumps(out, indent=1) + "\n")
     text = "\n".join(lines) + "\n"
