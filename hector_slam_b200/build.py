@@ -50,19 +50,22 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def build_cuda(force: bool = False, verbose: bool = False, extra: list[str] | None = None) -> str:
+def build_cuda(force: bool = False, verbose: bool = False, extra: list[str] | None = None, out: str | None = None) -> str:
+    """`extra` / `out`: a variant build (e.g. -DHSB_TLD4_OFFSET=0) next to the product library, for A/B comparisons
+    (scripts/alt_compare.py); load it with HSB_LIB_PATH."""
+    out = out or LIB
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "hector_slam_b200.h")]
-    if not force and _newer(LIB, srcs):
-        return LIB
+    if not force and _newer(out, srcs):
+        return out
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + (extra or []) + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB, os.path.join(CSRC, "hsb_api.cu")]
+        "-o", out, os.path.join(CSRC, "hsb_api.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    return LIB
+    return out
 
 
 def build_host(force: bool = False) -> str | None:

@@ -138,6 +138,16 @@ __device__ __forceinline__ void solve3(const Acc& s, float& o0, float& o1, float
 #ifndef HSB_UNROLL
 #define HSB_UNROLL 4
 #endif
+// 1: the gather takes the footprint's lower-left cell (ix, iy) as coordinates plus the texel offset (1, 1) carried by
+//    the instruction (SASS TLD4.AOFFI, one loop-invariant register) instead of computing (ix + 1, iy + 1) per endpoint.
+#ifndef HSB_TLD4_OFFSET
+#define HSB_TLD4_OFFSET 1
+#endif
+// 1: the nine H / dTr accumulations of an endpoint are predicated on "inside the map" (PTX @p fma) instead of sitting in
+//    a branch (BSSY / BRA / BSYNC per endpoint); out-of-map endpoints are rare, so nothing is gained by skipping them.
+#ifndef HSB_PRED_ACC
+#define HSB_PRED_ACC 1
+#endif
 
 struct PointPre {
   float rx, ry;   // rotated endpoint = d(q)/d(psi) terms: rotDeriv = rx*gy - ry*gx
@@ -194,11 +204,18 @@ __device__ __forceinline__ void point_address(const LevelRegs& L, float px, floa
     const float flx = truncf(qx), fly = truncf(qy);
     o.fx = __fsub_rn(qx, flx);                         // :298
     o.fy = __fsub_rn(qy, fly);
-    // texel centres (ix,iy)..(ix+1,iy+1): integer + 1.0 is exact in the unit's fixed-point
-    // coordinate conversion, so it cannot select a neighbouring footprint; clamp addressing makes
-    // any coordinate (also garbage from an outside point) safe
+    // texel centres (ix,iy)..(ix+1,iy+1): a gather at an INTEGER coordinate c selects texels c-1 and c, so the
+    // footprint is addressed as (ix + 1, iy + 1) — either added here, or (HSB_TLD4_OFFSET) as the instruction's
+    // immediate texel offset (1, 1).  Integers are exact in the unit's fixed-point coordinate conversion, so no
+    // neighbouring footprint can be selected; clamp addressing makes any coordinate (also garbage from an outside
+    // point) safe.
+#if HSB_TLD4_OFFSET
+    o.cx = flx;
+    o.cy = fly;
+#else
     o.cx = flx + 1.0f;
     o.cy = fly + 1.0f;
+#endif
   } else {
     const int ix = (int)qx, iy = (int)qy;              // :295 (garbage but harmless when !inside)
     o.fx = __fsub_rn(qx, (float)ix);
@@ -211,7 +228,14 @@ template <int MODE>
 __device__ __forceinline__ float4 point_fetch(const LevelRegs& L, const PointPre& p) {
   float4 v;  // (i0, i1, i2, i3) = cells (ix,iy) (ix+1,iy) (ix,iy+1) (ix+1,iy+1)
   if (MODE == MODE_TEX) {
+#if HSB_TLD4_OFFSET
+    float4 g;
+    asm("tld4.r.2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6}], {1, 1};"
+        : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w)
+        : "l"(L.tex), "f"(p.cx), "f"(p.cy));
+#else
     const float4 g = tex2Dgather<float4>(L.tex, p.cx, p.cy, 0);
+#endif
     v = make_float4(g.w, g.z, g.x, g.y);
   } else {
     const float* c = L.prob + p.idx;
@@ -256,7 +280,25 @@ __device__ __forceinline__ void point_accumulate(const PointPre& p, const float4
 #endif
   const float f = 1.0f - m;
   const float r = fmaf(p.rx, gy, -(p.ry * gx));
+#if HSB_PRED_ACC
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %13, 0;\n\t"
+      "@p fma.rn.f32 %0, %9, %12, %0;\n\t"     // d0  += gx * f
+      "@p fma.rn.f32 %1, %10, %12, %1;\n\t"    // d1  += gy * f
+      "@p fma.rn.f32 %2, %11, %12, %2;\n\t"    // d2  += r  * f
+      "@p fma.rn.f32 %3, %9, %9, %3;\n\t"      // h00 += gx * gx
+      "@p fma.rn.f32 %4, %10, %10, %4;\n\t"    // h11 += gy * gy
+      "@p fma.rn.f32 %5, %11, %11, %5;\n\t"    // h22 += r  * r
+      "@p fma.rn.f32 %6, %9, %10, %6;\n\t"     // h01 += gx * gy
+      "@p fma.rn.f32 %7, %9, %11, %7;\n\t"     // h02 += gx * r
+      "@p fma.rn.f32 %8, %10, %11, %8;\n\t"    // h12 += gy * r
+      "}"
+      : "+f"(a.d0), "+f"(a.d1), "+f"(a.d2), "+f"(a.h00), "+f"(a.h11), "+f"(a.h22), "+f"(a.h01), "+f"(a.h02), "+f"(a.h12)
+      : "f"(gx), "f"(gy), "f"(r), "f"(f), "r"((unsigned)p.inside));
+  if (false) {
+#else
   if (p.inside) {  // the translation unit is built with -fmad=false: fused operations are explicit
+#endif
     a.d0 = fmaf(gx, f, a.d0);
     a.d1 = fmaf(gy, f, a.d1);
     a.d2 = fmaf(r, f, a.d2);
