@@ -294,7 +294,7 @@ def test_non_square_map_other_resolution_and_start(hsb_lib, pyoracle, oracle_kin
     for l in range(2):
         d = np.abs(rep.download_level(l) - orc.get_logodds(l))
         report(f"planes[non-square level {l}, mode {mode}]: {int((d > 1e-5).sum())} cells differ of {int((orc.get_logodds(l) != 0).sum())} touched")
-        assert (d > 1e-5).sum() <= max(3, int(5e-4 * (d.size))), (l, int((d > 1e-5).sum()))
+        assert (d > 1e-5).sum() <= 2, (l, int((d > 1e-5).sum()))   # observed: 0 of 354 001 / 95 400 touched cells
         rep.upload_level(l, orc.get_logodds(l))      # continue from identical planes
     test_poses = world.sample_free_poses(64, rng, margin=0.8)
     pts, offs = synth.make_scan_batch(world, test_poses, noise_seed=5, scale_to_map=scale)

@@ -13,13 +13,19 @@ pytestmark = pytest.mark.gpu
 PLANE_TOL = 1e-5
 
 
-def compare_planes(got, want, what, max_bad_frac=2e-4):
+# Observed on the B200 (gpurun_out/parity_report.log, round 2): ZERO cells beyond 1e-5 in every comparison of this file
+# (66 k - 116 k touched cells each, largest difference 4.8e-7 = the ((l+lf)-lf)+lo vs l+lo ulp).  The bar is the survey's
+# own observation for the reference against itself under reordering, 2 cells (2 in 13 M touches) — an
+# off-by-one-cell bug in a beam end or a Bresenham carry moves hundreds of cells and cannot hide in it.
+MAX_BAD_CELLS = 2
+
+
+def compare_planes(got, want, what, max_bad=MAX_BAD_CELLS):
     diff = np.abs(got.astype(np.float64) - want.astype(np.float64))
     bad = diff > PLANE_TOL
     touched = max(1, int((want != 0).sum()))
-    frac = bad.sum() / touched
     report(f"planes[{what}]: {int(bad.sum())} cells differ by > {PLANE_TOL} of {touched} touched (max |diff| {float(diff.max()):.3e})")
-    assert frac <= max_bad_frac, (what, int(bad.sum()), touched, float(diff.max()))
+    assert bad.sum() <= max_bad, (what, int(bad.sum()), touched, float(diff.max()))
     return int(bad.sum())
 
 
@@ -106,7 +112,7 @@ def test_slam_run(hsb_lib, mode):
         hint = pose
     final = golden_planes(g, "final")
     for l in range(3):
-        compare_planes(rep.download_level(l), final[l], f"final level {l}", max_bad_frac=2e-3)
+        compare_planes(rep.download_level(l), final[l], f"final level {l}")
     rep.reset()
     for l in range(3):
         assert np.all(rep.download_level(l) == 0) and np.all(rep.download_prob(l) == 0.5)
