@@ -96,6 +96,8 @@ struct hsb_handle {
   // tuning
   int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1;
   DevBuf d_trace;
+  bool map_write_pending = false;   // a nowait SLAM step's map write may still be running on `stream`
+  unsigned step_seq = 0;   // sequence number of the fused SLAM steps (host polling, hsb_slam_update_nowait)
   int trace_scans = 0;
   int last_shape[6] = {0, 0, 0, 0, 0, 0};  // W, G, U, staged points per scan (0 = none), grid, resident CTAs / SM
   uint64_t launches = 0;
@@ -347,6 +349,11 @@ int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t 
 }
 
 int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
+  if (h->map_write_pending && st != h->stream) {
+    // hsb_slam_update_nowait left a map write running on the handle's stream: a match on another stream waits for it
+    HSB_CUDA(h, cudaEventRecord(h->ev_sync[0], h->stream));
+    HSB_CUDA(h, cudaStreamWaitEvent(st, h->ev_sync[0], 0));
+  }
   int W = h->tune_warps_per_scan, G = h->tune_scans_per_block;
   if (W <= 0) {
     // Measured on B200 (profiles/r01_sweep_batches.log, r01_sweep_large_batches.log): one warp per
@@ -754,7 +761,7 @@ int hsb_world_coords_pose(const hsb_handle* h, int level, const float map[3], fl
 
 static int match_device(hsb_handle* h, int B, const float* d_hints, const float* d_pts, const int* d_offsets, int n_shared,
                         int max_points_per_scan, float* d_out_poses, float* d_out_cov, float* gate_state, const float* gate_in,
-                        float* gate_out_host, cudaStream_t stream) {
+                        float* gate_out_host, cudaStream_t stream, unsigned* seq_host = nullptr, unsigned seq_value = 0) {
   if (!h || B < 0 || !d_hints || !d_out_poses) return HSB_ERR_INVALID_ARG;
   if (B == 0) return HSB_OK;
   if (!d_offsets && n_shared < 0) return fail(h, HSB_ERR_INVALID_ARG, "shared-scan mode needs n_shared >= 0");
@@ -772,6 +779,8 @@ static int match_device(hsb_handle* h, int B, const float* d_hints, const float*
   P.gate_state = gate_state;   // fused SLAM step only (B == 1)
   P.gate_in = gate_in;
   P.gate_out_host = gate_out_host;
+  P.seq_host = seq_host;
+  P.seq_value = seq_value;
   int max_n = d_offsets ? max_points_per_scan : n_shared;
   if (max_n < 0) max_n = 0;
   return launch_match(h, P, max_n, stream);
@@ -1385,8 +1394,8 @@ int hsb_set_map_update_min_angle_diff(hsb_handle* h, float min_angle) {
   return HSB_OK;
 }
 
-int hsb_slam_update(hsb_handle* h, const float hint[3], const float* pts, int n, const float origo[2],
-                    int map_without_matching, float out_pose[3], float cov_inout[9], int* map_updated) {
+static int slam_update_impl(hsb_handle* h, const float hint[3], const float* pts, int n, const float origo[2],
+                            int map_without_matching, float out_pose[3], float cov_inout[9], int* map_updated, bool wait_map) {
   if (!h || !hint || !out_pose || n < 0 || (n > 0 && !pts)) return HSB_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
   int s;
@@ -1401,8 +1410,13 @@ int hsb_slam_update(hsb_handle* h, const float hint[3], const float* pts, int n,
   DevBuf& pbuf = map_without_matching ? h->d_upd_pts : h->d_last_pts;
   const float header[6] = {hint[0], hint[1], hint[2], h->min_dist, h->min_angle, map_without_matching ? 1.f : 0.f};
   // results (pose, flag, Hessian) are written into mapped host memory by the kernels themselves: the step is one
-  // host-to-device copy, four launches and one synchronize
+  // host-to-device copy and three launches (match with the gate in its epilogue, mark, apply — the latter two with
+  // programmatic dependent launch)
   const bool host_out = h->tune_host_out != 0;
+  const bool poll = host_out && !wait_map;   // return when the pose has arrived; the map write continues on the stream
+  volatile unsigned* seq = reinterpret_cast<volatile unsigned*>(h->h_pin + 22);
+  unsigned* seq_dev = reinterpret_cast<unsigned*>(h->h_pin_dev + 22);
+  const unsigned seq_value = ++h->step_seq;
   if ((s = upload_scan(h, pbuf, header, 6, pts, n, st)) != HSB_OK) return s;
   const float* d_hdr = scan_header(pbuf);
   const float* d_pose_in = d_hdr;  // the hint, unless matched below
@@ -1412,21 +1426,47 @@ int hsb_slam_update(hsb_handle* h, const float hint[3], const float* pts, int n,
     h->last_origo[1] = origo ? origo[1] : 0.f;
     // :78 match, and :83-89 the gate in the same kernel's epilogue (an empty scan still passes through it: pose = hint)
     s = match_device(h, 1, d_hdr, scan_points(pbuf), nullptr, n, n, d_s + 8, host_out ? h->h_pin_dev + 12 : d_s + 12, d_gate,
-                     d_hdr + 3, host_out ? h->h_pin_dev + 8 : nullptr, st);
+                     d_hdr + 3, host_out ? h->h_pin_dev + 8 : nullptr, st, poll ? seq_dev : nullptr, seq_value);
     if (s != HSB_OK) return s;
   } else {
-    hsb::slam_gate_kernel<<<1, 32, 0, st>>>(d_gate, d_hdr + 3, d_pose_in, d_s + 8, host_out ? h->h_pin_dev + 8 : nullptr);  // :80, :89
+    hsb::slam_gate_kernel<<<1, 32, 0, st>>>(d_gate, d_hdr + 3, d_pose_in, d_s + 8, host_out ? h->h_pin_dev + 8 : nullptr,
+                                            poll ? seq_dev : nullptr, seq_value);  // :80, :89
     h->launches += 1;
     HSB_CUDA(h, cudaGetLastError());
   }
   if ((s = enqueue_update_by_scan(h, reinterpret_cast<const float2*>(scan_points(pbuf)), n, origo, nullptr, d_s + 8, d_gate + 3)) != HSB_OK)  // :91
     return s;
-  if (!host_out) HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 8, d_s + 8, 13 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  HSB_CUDA(h, cudaStreamSynchronize(st));  // :93 onMapUpdated — the probability plane is current
+  if (poll) {
+    // the pose is all the caller needs now; every later call on this handle is stream-ordered behind the map write
+    unsigned spins = 0;
+    while (*seq != seq_value) {
+      if ((++spins & 0xfffu) == 0) {   // every 4096 polls make sure the stream has not died underneath us
+        cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return fail(h, HSB_ERR_CUDA, "stream failed: %s", cudaGetErrorString(e));
+        if (e == cudaSuccess && *seq != seq_value) return fail(h, HSB_ERR_CUDA, "fused step finished without publishing its pose");
+      }
+    }
+    __sync_synchronize();
+    h->map_write_pending = true;
+  } else {
+    if (!host_out) HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 8, d_s + 8, 13 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HSB_CUDA(h, cudaStreamSynchronize(st));  // :93 onMapUpdated — the probability plane is current
+    h->map_write_pending = false;
+  }
   memcpy(out_pose, h->h_pin + 8, 3 * sizeof(float));
   if (map_updated) *map_updated = h->h_pin[11] != 0.f;
   if (cov_inout && n > 0 && !map_without_matching) memcpy(cov_inout, h->h_pin + 12, 9 * sizeof(float));
   return HSB_OK;
+}
+
+int hsb_slam_update(hsb_handle* h, const float hint[3], const float* pts, int n, const float origo[2],
+                    int map_without_matching, float out_pose[3], float cov_inout[9], int* map_updated) {
+  return slam_update_impl(h, hint, pts, n, origo, map_without_matching, out_pose, cov_inout, map_updated, true);
+}
+
+int hsb_slam_update_nowait(hsb_handle* h, const float hint[3], const float* pts, int n, const float origo[2],
+                           int map_without_matching, float out_pose[3], float cov_inout[9], int* map_updated) {
+  return slam_update_impl(h, hint, pts, n, origo, map_without_matching, out_pose, cov_inout, map_updated, false);
 }
 
 int hsb_set_last_map_update_pose(hsb_handle* h, const float pose[3]) {
@@ -1483,6 +1523,7 @@ int hsb_on_map_updated(hsb_handle* h) {
   if (!h) return HSB_ERR_INVALID_ARG;
   DeviceGuard guard(h->device);
   HSB_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->map_write_pending = false;
   return HSB_OK;
 }
 

@@ -917,6 +917,10 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
         c[6] = last.h02; c[7] = last.h12; c[8] = last.h22;
       }
     }
+    if (t == 0 && P.seq_host) {   // fused SLAM step: results are in mapped host memory — tell the polling host
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned*>(P.seq_host) = P.seq_value;
+    }
     if (cap > 0) group_sync<W>(g);  // everyone done with spts before the next bulk copy lands
   }
   if (pace && t == 0) prog[g] = 0x7fffffff;   // this group is done: nobody waits for it any more

@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+__device__ __forceinline__ void pdl_launch_dependents_early() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- K2 -----------------------------------------------------------------------------------------
 
 // HectorSlamProcessor::update's gate (slam_main/HectorSlamProcessor.h:83-95) evaluated on the device so that a
@@ -186,8 +188,15 @@ __global__ void __launch_bounds__(256)
 // pose_out (device) and pose_out_host (mapped host memory, may be null) receive the step's pose (the matched
 // pose, or the hint when matching is skipped) and, in [3], a copy of the flag.
 __global__ void slam_gate_kernel(float* __restrict__ state, const float* __restrict__ in, const float* pose_in,
-                                 float* pose_out, float* pose_out_host) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) slam_gate(state, in, pose_in[0], pose_in[1], pose_in[2], pose_out, pose_out_host);
+                                 float* pose_out, float* pose_out_host, unsigned* seq_host, unsigned seq_value) {
+  pdl_launch_dependents_early();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    slam_gate(state, in, pose_in[0], pose_in[1], pose_in[2], pose_out, pose_out_host);
+    if (seq_host) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned*>(seq_host) = seq_value;
+    }
+  }
 }
 
 // Per-level frame of one updateByScan call: the pose as Translation(x,y)*Rotation(psi) in this level's cells and

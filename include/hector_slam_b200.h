@@ -244,6 +244,15 @@ int hsb_set_map_update_min_angle_diff(hsb_handle* h, float min_angle);
 int hsb_slam_update(hsb_handle* h, const float pose_hint_world[3], const float* points_xy, int n,
                     const float origo[2], int map_without_matching, float out_pose_world[3],
                     float cov_inout[9], int* map_updated);
+/* The same step, returning as soon as the step's pose, covariance and gate decision have arrived in host memory (the
+ * match kernel publishes them itself; the host polls a sequence number instead of synchronising the stream) — the map
+ * write, if the gate fired, is still running on the handle's stream.  Every later call on the handle is ordered
+ * behind it, so results are identical to hsb_slam_update; hsb_on_map_updated(h) is the explicit completion point
+ * (what HectorSlamProcessor::update calls at :93).  This is the latency a robot sees for its pose estimate; the
+ * sustained step rate is that of hsb_slam_update. */
+int hsb_slam_update_nowait(hsb_handle* h, const float pose_hint_world[3], const float* points_xy, int n,
+                           const float origo[2], int map_without_matching, float out_pose_world[3],
+                           float cov_inout[9], int* map_updated);
 /* lastMapUpdatePose of the fused step (HectorSlamProcessor.h:151) */
 int hsb_get_last_map_update_pose(hsb_handle* h, float out[3]);
 /* ... and its setter, for a host that wrote the map itself (hsb_update_by_scan) between fused steps: the gate of the

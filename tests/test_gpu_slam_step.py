@@ -146,3 +146,35 @@ def test_map_writer_on_unaligned_rows(hsb_lib, pyoracle, size):
         assert (diff > 1e-5).sum() <= max(3, int(2e-3 * (got != 0).sum())), (size, l, int((diff > 1e-5).sum()))
     rep.close()
     orc.close()
+
+
+def test_nowait_step_equals_the_synchronous_step(hsb_lib):
+    """hsb_slam_update_nowait returns when the pose has arrived and leaves the map write on the stream: the whole run —
+    poses, gate decisions, final planes — must equal the synchronous call's, also when a batch match on other streams
+    follows a step immediately (it has to wait for the pending map write)."""
+    from hector_slam_b200 import capi
+
+    g = load_golden("slam3.npz")
+
+    def run(nowait):
+        rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+        rep.setMapUpdateMinDistDiff(0.05)
+        rep.setMapUpdateMinAngleDiff(0.02)
+        hint, traj, flags, probes = g["first_hint"], [], [], []
+        for k in range(g["scans"].shape[0]):
+            hint, cov, upd = rep.slam_update(hint, g["scans"][k], nowait=nowait)
+            traj.append(hint)
+            flags.append(upd)
+            if k % 3 == 2:   # a batch call straight after the step: sees the map INCLUDING this step's write
+                P, _ = rep.match_batch(np.repeat(hint[None], 4, axis=0), g["scans"][k], None)
+                probes.append(P[0])
+        rep.onMapUpdated()
+        planes = [rep.download_level(l) for l in range(3)]
+        rep.close()
+        return np.asarray(traj), flags, np.asarray(probes), planes
+
+    a, b = run(False), run(True)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] and np.array_equal(a[2], b[2])
+    assert any(a[1]) and not all(a[1])
+    for l in range(3):
+        assert np.array_equal(a[3][l], b[3][l])
