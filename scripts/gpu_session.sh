@@ -5,7 +5,7 @@ tag=${1:-s}
 out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
-echo "== pytest (full gpu suite)"; timeout 900 python -m pytest tests -m gpu -q -x > $out/${tag}_pytest.log 2>&1; tail -3 $out/${tag}_pytest.log
+echo "== pytest (full gpu suite)"; timeout 900 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; tail -3 $out/${tag}_pytest.log
 echo "== k1 probe"; timeout 300 python scripts/k1_probe.py 4096 > $out/${tag}_k1_probe.log 2>&1; head -40 $out/${tag}_k1_probe.log
 echo "== A/B: instruction-level variants must not change a bit"; timeout 600 python scripts/alt_compare.py > $out/${tag}_alt_compare.log 2>&1; tail -25 $out/${tag}_alt_compare.log
 echo "== bench N=1"; timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 600 $out/${tag}_bench.err; head -c 1500 $out/${tag}_bench.json
