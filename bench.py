@@ -586,11 +586,13 @@ def main():
         line.update(extras)
         if world_size == 1 and not args.no_extras:
             line.update(extra_config3(capi, synth, new_rep, args))
-        print(json.dumps(line), flush=True)
     rep.close()
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:   # after NCCL's teardown, so that with NCCL_DEBUG=INFO the JSON line is still the last line on stdout
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
