@@ -94,7 +94,7 @@ struct hsb_handle {
   DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
   float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1, tune_auto_group = 0;
   DevBuf d_trace;
   bool map_write_pending = false;   // a nowait SLAM step's map write may still be running on `stream`
   unsigned step_seq = 0;   // sequence number of the fused SLAM steps (host polling, hsb_slam_update_nowait)
@@ -236,7 +236,8 @@ void fill_level_dev(const hsb_handle* h, int l, HsbLevelDev& d) {
 
 // ---- match launch -----------------------------------------------------------------------------
 template <int W, int G, int MODE, int U, bool PACK>
-int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
+int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int Gr) {
+  if (Gr <= 0 || Gr > G) Gr = G;   // groups per CTA actually launched (a G-group kernel runs with fewer: see launch_match)
   const size_t header = hsb::MatchSmem<W, G>::kHeaderBytes;
   auto kern = hsb::match_kernel<W, G, MODE, U, PACK>;
   constexpr size_t kMaxDyn = 232448;   // dynamic shared memory one CTA may ask for (227 KB)
@@ -252,7 +253,7 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
     HSB_CUDA(h, cudaFuncGetAttributes(&fa, kern));
     regs = fa.numRegs > 0 ? fa.numRegs : 32;
   }
-  const int threads = W * G * 32;
+  const int threads = W * Gr * 32;
   auto resident = [&](size_t smem_bytes) {
     int blocks = std::min(32, 2048 / threads);
     blocks = std::min(blocks, 65536 / (((regs + 7) / 8 * 8) * threads));
@@ -262,12 +263,12 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
   // slots (a multiple of the group size, + 2 for the alignment head) that fit when `ctas` CTAs share an SM
   auto cap_for = [&](long ctas) {
     const long budget = std::min<long>((long)kMaxDyn, (long)kMaxDyn / ctas - 1024) - (long)header;
-    int pts = (int)(budget / 8 / G);
+    int pts = (int)(budget / 8 / Gr);
     pts = (pts - 2) / gt * gt;
     return pts >= 4 * gt ? pts + 2 : 0;
   };
   const bool may_split = h->tune_partial && !PACK && !fused;   // a staged PREFIX is allowed
-  if (cap > 0 && header + (size_t)G * cap * 8 > kMaxDyn) {        // the CTA's scans do not fit whole
+  if (cap > 0 && header + (size_t)Gr * cap * 8 > kMaxDyn) {        // the CTA's scans do not fit whole
     if (fused) return fail(h, HSB_ERR_UNSUPPORTED, "scan too long for the fused conversion (%d points)", max_n);
     cap = may_split ? cap_for(1) : 0;
   }
@@ -277,16 +278,16 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
     // scans staged but does fit WITHOUT (one wave instead of one and a bit), stage only the prefix
     // of each scan that the shared memory of a one-wave residency affords and read the rest through
     // L1 (tuning "partial" = 0: stage nothing in that case).
-    const long groups = ((long)P.B + G - 1) / G;
-    const long slots_staged = (long)resident(header + (size_t)G * cap * 8) * h->sm_count;
+    const long groups = ((long)P.B + Gr - 1) / Gr;
+    const long slots_staged = (long)resident(header + (size_t)Gr * cap * 8) * h->sm_count;
     const long slots_plain = (long)resident(header) * h->sm_count;
     if (groups > slots_staged && groups <= slots_plain)
       cap = may_split ? cap_for((groups + h->sm_count - 1) / h->sm_count) : 0;
   }
   P.prefetch = h->tune_prefetch;
-  P.pace_slack = h->tune_pace;
+  P.pace_slack = h->tune_pace > 0 ? h->tune_pace : P.pace_slack_req;
   P.pts_cap = cap;
-  size_t smem = header + (size_t)G * cap * 8;
+  size_t smem = header + (size_t)Gr * cap * 8;
   if (smem > 48 * 1024) {
     HSB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -308,11 +309,11 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
     h->trace_scans = P.B;
   }
   const int seq = h->tune_seq > 0 ? h->tune_seq : 1;  // scans each group handles one after the other
-  int grid = (P.B + G * seq - 1) / (G * seq);
-  kern<<<grid, W * G * 32, smem, st>>>(P);
+  int grid = (P.B + Gr * seq - 1) / (Gr * seq);
+  kern<<<grid, W * Gr * 32, smem, st>>>(P);
   h->launches++;
   {
-    const int shape[6] = {W, G, U, cap > 0 ? (cap > max_n ? max_n : ((cap - 2) / (W * 32)) * (W * 32)) : 0, grid, resident(smem)};
+    const int shape[6] = {W, Gr, U, cap > 0 ? (cap > max_n ? max_n : ((cap - 2) / (W * 32)) * (W * 32)) : 0, grid, resident(smem)};
     memcpy(h->last_shape, shape, sizeof(shape));
   }
   HSB_CUDA(h, cudaGetLastError());
@@ -320,11 +321,11 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st)
 }
 
 template <int MODE>
-int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int W, int G, int U) {
+int launch_match_mode(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int W, int G, int U, int Gr) {
 #define HSB_CASE(w, g, u)                                                                          \
   if (W == w && G == g && U == u) {                                                                \
-    if (MODE == hsb::MODE_TEX && h->tune_packed) return launch_match_t<w, g, hsb::MODE_TEX, u, true>(h, P, max_n, st); \
-    return launch_match_t<w, g, MODE, u, false>(h, P, max_n, st);                                  \
+    if (MODE == hsb::MODE_TEX && h->tune_packed) return launch_match_t<w, g, hsb::MODE_TEX, u, true>(h, P, max_n, st, Gr); \
+    return launch_match_t<w, g, MODE, u, false>(h, P, max_n, st, Gr);                              \
   }
   // launch shapes kept after the sweeps in profiles/ (groups per CTA > 1 and more than 16 warps
   // per scan never won anywhere and were dropped)
@@ -368,10 +369,23 @@ int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
     W = 1;
     while (W * 2 <= want && W < 8) W *= 2;
   }
-  if (G <= 0) G = 1;
+  int Gr = 0;   // 0: as many groups per CTA as the instantiation has
+  if (G <= 0) {
+    G = 1;
+    // One-wave batches of one-warp scans (tuning "auto_group"): ONE CTA per SM holding ceil(B / SMs) <= 28 scans, paced
+    // (match_kernel.cuh) — all scans of an SM advance together and end together instead of trailing off over the last
+    // third of the launch (profiles/r02_k1_timeline.md).  Larger batches keep one scan per CTA: finished warps are
+    // replaced at once there and a CTA-wide drain would cost more than the tail it removes.
+    const long Bs = h->shape_batch > 0 ? h->shape_batch : P.B;
+    if (h->tune_auto_group && W == 1 && !P.ranges && !P.cloud && Bs == P.B && Bs <= (long)h->sm_count * 28) {
+      G = 28;
+      Gr = (int)((Bs + h->sm_count - 1) / h->sm_count);
+      if (P.pace_slack_req == 0) P.pace_slack_req = h->tune_auto_group;
+    }
+  }
   int U = h->tune_unroll > 0 ? h->tune_unroll : 4;
-  if (h->gather_mode == HSB_GATHER_TEX) return launch_match_mode<hsb::MODE_TEX>(h, P, max_n, st, W, G, U);
-  return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G, U);
+  if (h->gather_mode == HSB_GATHER_TEX) return launch_match_mode<hsb::MODE_TEX>(h, P, max_n, st, W, G, U, Gr);
+  return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G, U, Gr);
 }
 
 // Copy/compute pipeline of the host-buffer batch calls: chunk c's host->device copy overlaps the
@@ -729,6 +743,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "pace")) h->tune_pace = value;
   else if (!strcmp(key, "time_update")) h->tune_time_update = value;
   else if (!strcmp(key, "pdl")) h->tune_pdl = value;
+  else if (!strcmp(key, "auto_group")) h->tune_auto_group = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }

@@ -696,6 +696,7 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
   float2* spts_all = reinterpret_cast<float2*>(smem_raw + MatchSmem<W, G>::kHeaderBytes);
 
   constexpr int GT = W * 32;  // threads per group
+  const int Gr = blockDim.x / GT;   // groups actually launched per CTA (<= G: the launcher may run a G-group kernel with fewer)
   const int g = threadIdx.x / GT;
   const int t = threadIdx.x - g * GT;
   const int w = t >> 5;
@@ -723,12 +724,12 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
     if (threadIdx.x < 32) prog[threadIdx.x] = 0x7fffffff;   // slots of absent / finished groups never hold anyone back
   }
   __syncthreads();
-  if (pace && t == 0 && blockIdx.x * G + g < P.B) prog[g] = 0;
+  if (pace && t == 0 && blockIdx.x * Gr + g < P.B) prog[g] = 0;
   if (G > 1) __syncthreads();
 
   uint32_t phase = 0;
   int red_flip = 0;
-  for (int scan = blockIdx.x * G + g; scan < P.B; scan += gridDim.x * G) {
+  for (int scan = blockIdx.x * Gr + g; scan < P.B; scan += gridDim.x * Gr) {
     int beg, n;
     if (P.cloud) {
       beg = P.cloud_offsets[scan];

@@ -50,11 +50,14 @@ def timed(iters=20):
     return min(best), float(np.median(best))
 
 
-base = dict(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=0, prefetch=0, trace=0, seq=0, pace=0)
+base = dict(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=0, prefetch=0, trace=0, seq=0, pace=0, auto_group=0)
 variants = [
     ("default", {}),
     ("G=1 partial staging", dict(partial=1)),
 ]
+for ag in (1, 2, 3):
+    variants.append((f"auto_group pace={ag} staged prefix", dict(auto_group=ag, partial=1)))
+    variants.append((f"auto_group pace={ag} unstaged", dict(auto_group=ag, stage_smem=0)))
 for G in (28, 14, 7, 2):
     for pace in (0, 1, 2, 4):
         for stage, part in ((0, 0), (1, 1)):
