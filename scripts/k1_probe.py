@@ -63,6 +63,8 @@ for G in (28, 14, 7, 2):
         for stage, part in ((0, 0), (1, 1)):
             variants.append((f"G={G} pace={pace} " + ("staged prefix" if stage else "unstaged"),
                              dict(warps_per_scan=1, scans_per_block=G, pace=pace, stage_smem=stage, partial=part)))
+if B > 8192:   # many waves: only the staging question matters
+    variants = [("default", {}), ("always fully staged", dict(stage_smem=2)), ("never staged", dict(stage_smem=0))]
 ref = None
 for name, kw in variants:
     t = dict(base)
@@ -139,6 +141,10 @@ def slot_study():
         print(f"  warpid {slot:2d} (scheduler {slot % 4}): n={int(sel.sum()):4d} p50 {np.median(d[sel]):6.1f} us")
 
 
+if B > 8192:
+    rep.set_tuning(**base)
+    rep.close()
+    sys.exit(0)
 timeline("default (G=1 unstaged)", {})
 slot_study()
 timeline("G=28 pace=1 staged prefix", dict(warps_per_scan=1, scans_per_block=28, pace=1, stage_smem=1, partial=1))
