@@ -171,7 +171,13 @@ struct LevelRegs {
 // kernel, measured in the round-1 SASS).  A warp reduction (redux.sync -> REDUX, whose result lands in a uniform
 // register) of the — identical — per-lane copies makes the uniformity visible: the TLD4s take the handle from UR
 // directly.  Must be called with all 32 lanes converged (every caller does, once per level).
+#ifndef HSB_UNIFORM_HANDLE
+#define HSB_UNIFORM_HANDLE 1
+#endif
 __device__ __forceinline__ cudaTextureObject_t uniform_handle(cudaTextureObject_t t) {
+#if !HSB_UNIFORM_HANDLE
+  return t;
+#endif
   const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(t & 0xffffffffull));
   const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(t >> 32));
   return ((cudaTextureObject_t)hi << 32) | (cudaTextureObject_t)lo;

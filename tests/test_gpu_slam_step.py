@@ -158,8 +158,8 @@ def test_nowait_step_equals_the_synchronous_step(hsb_lib):
 
     def run(nowait):
         rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
-        rep.setMapUpdateMinDistDiff(0.05)
-        rep.setMapUpdateMinAngleDiff(0.02)
+        rep.setMapUpdateMinDistDiff(0.2)     # the trajectory advances 0.155 m per scan: the gate fires every other step
+        rep.setMapUpdateMinAngleDiff(0.9)
         hint, traj, flags, probes = g["first_hint"], [], [], []
         for k in range(g["scans"].shape[0]):
             hint, cov, upd = rep.slam_update(hint, g["scans"][k], nowait=nowait)
