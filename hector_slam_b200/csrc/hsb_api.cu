@@ -29,8 +29,6 @@ struct Level {
   uint32_t stamp_base = 0;
   int* scratch = nullptr;      // two slots of 8 ints for the two-phase writer (see HsbUpdateLevelDev)
   int parity = 0;              // slot the NEXT map write of this level uses
-  unsigned* list = nullptr;    // cells marked by the scan being written
-  unsigned list_cap = 0;
   cudaArray_t arr = nullptr;
   cudaTextureObject_t tex = 0;
   cudaSurfaceObject_t surf = 0;
@@ -433,7 +431,6 @@ int destroy_level(hsb_handle* h, Level& L) {
   if (L.prob) cudaFree(L.prob);
   if (L.stamp) cudaFree(L.stamp);
   if (L.scratch) cudaFree(L.scratch);
-  if (L.list) cudaFree(L.list);
   L = Level();
   (void)h;
   return HSB_OK;
@@ -588,10 +585,6 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
       const int clean[16] = {0, INT_MAX, INT_MAX, -1, -1, 0, 0, 0, 0, INT_MAX, INT_MAX, -1, -1, 0, 0, 0};
       HSB_CUDA_C(cudaMemcpy(L.scratch, clean, sizeof(clean), cudaMemcpyHostToDevice));
     }
-    // a scan cannot mark more cells than the level has; 4 M entries (16 MB) cover any real scan, beyond that the
-    // apply phase falls back to sweeping the bounding box
-    L.list_cap = (unsigned)std::min<size_t>(n, (size_t)4 << 20);
-    HSB_CUDA_C(cudaMalloc(&L.list, (size_t)L.list_cap * sizeof(unsigned)));
     if (h->gather_mode == HSB_GATHER_TEX) {
       cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
       HSB_CUDA_C(cudaMallocArray(&L.arr, &desc, dx, dy, cudaArrayTextureGather | cudaArraySurfaceLoadStore));
@@ -1344,8 +1337,6 @@ static void fill_update_level(hsb_handle* h, int l, HsbUpdateLevelDev& d) {
   d.dirty = L.dirty;
   d.scratch = L.scratch;
   d.slot = L.parity;
-  d.list = L.list;
-  d.list_cap = L.list_cap;
 }
 
 // MapRepMultiMap::updateByScan (MapRepMultiMap.h:134-147) as launches on h->stream; level 0 reads `d_pts0`,

@@ -76,13 +76,11 @@ struct HsbUpdateLevelDev {
   uint32_t stamp_base;       // this scan's stamps: base+1 free, base+2 occupied
   int active;
   int* dirty;                // two rectangles {xmin, ymin, xmax, ymax} of cells written since their last reset (device)
-  // per-scan scratch of the two-phase writer (device): two slots of 8 ints, {count, x0, y0, x1, y1, -, -, -}; the mark
-  // phase of a scan fills slot `slot` (number of cells it marked first + bounding box of start and end cells), the apply
-  // phase consumes it and clears the OTHER slot for the next scan
+  // per-scan scratch of the two-phase writer (device): two slots of 8 ints, {-, x0, y0, x1, y1, -, -, -}; the mark
+  // phase of a scan leaves the bounding box of its start and end cells in slot `slot`, the apply phase consumes it and
+  // clears the OTHER slot for the next scan
   int* scratch;
   int slot;
-  unsigned* list;            // cells marked by this scan, each exactly once (offsets into the level's planes)
-  unsigned list_cap;
 };
 
 struct HsbUpdateParams {

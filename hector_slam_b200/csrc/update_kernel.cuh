@@ -243,23 +243,14 @@ __device__ __forceinline__ bool beam_end(const HsbUpdateLevelDev& L, const BeamF
   return true;
 }
 
-// Warp-aggregated append: the active lanes of the warp that call this get consecutive slots of `list` with one atomic.
-__device__ __forceinline__ void list_append(unsigned* __restrict__ list, int* __restrict__ count, unsigned cap, unsigned value) {
-  const unsigned active = __activemask();
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(active) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(count, __popc(active));
-  base = __shfl_sync(active, base, leader);
-  const unsigned idx = (unsigned)base + (unsigned)__popc(active & ((1u << lane) - 1u));
-  if (idx < cap) list[idx] = value;
-}
-
 // MARK: a team of TEAM warps per beam; blockIdx.y = level.  Team lanes stride along the line, four cells per
-// lane in flight (the loop is bound by the L2 round trip of the stamp test, not by arithmetic).  The thread whose
-// atomicMax is the FIRST to stamp a cell in this scan also appends the cell to the scan's list, so the apply phase
-// visits exactly the touched cells (no sweep, one owner per cell by construction).  The bounding box of the start
-// cell and the beams' end cells goes to the scratch slot (dirty rectangles; fallback sweep if the list overflowed).
+// lane in flight (the loop is bound by the L2 round trip of the stamp test, not by arithmetic); the stamps are raised
+// with result-less atomics (RED.MAX: nothing waits for them).  The bounding box of the start cell and the beams' end
+// cells goes to the scan's scratch slot (4 atomics per warp): the apply phase sweeps exactly that box and the dirty
+// rectangles are fed from it.  (A variant that also compacted the first-marked cells into a list for the apply phase
+// was measured in round 2: it needs the atomics' return values — two more dependent L2 round trips per iteration —
+// and made mark + apply slower, 29 us against 23 us; at a scan's size the box sweep is launch- and latency-sized,
+// not bandwidth-sized.)
 // Programmatic dependent launch (sm_90+): mark and apply are launched with programmatic stream serialisation, i.e.
 // their CTAs may become resident while the previous kernel of the stream (the match kernel of a fused SLAM step, or
 // mark before apply) is still running; griddepcontrol.wait blocks until that kernel has completed and its writes are
@@ -331,14 +322,9 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
       }
 #pragma unroll
       for (int k = 0; k < U; ++k)
-        if (v[k] < free_s) {                                       // bresenhamCellFree :216-224
-          if (atomicMax(L.stamp + off[k], free_s) < free_s) list_append(L.list, slot, L.list_cap, off[k]);
-        }
+        if (v[k] < free_s) atomicMax(L.stamp + off[k], free_s);   // bresenhamCellFree :216-224
     }
-    if (tlane == 0) {                                              // bresenhamCellOcc :226-241, :211-212
-      const unsigned eoff = (unsigned)y1 * (unsigned)L.sx + (unsigned)x1;
-      if (atomicMax(L.stamp + eoff, occ_s) < free_s) list_append(L.list, slot, L.list_cap, eoff);
-    }
+    if (tlane == 0) atomicMax(L.stamp + (unsigned)y1 * (unsigned)L.sx + (unsigned)x1, occ_s);   // bresenhamCellOcc :226-241, :211-212
   }
   // bounding box of this warp's beams (+ the common start cell) -> scratch slot, 4 atomics per warp
 #pragma unroll
@@ -356,10 +342,11 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
   }
 }
 
-// APPLY: every cell the scan marked is in its list exactly once: a grid-stride pass over the list applies the
-// log-odds update and rewrites the probability (and the texture twin) — no atomics, one owner per cell, deterministic
-// values whatever the list order.  Should the list have overflowed (more cells than its capacity), the pass falls back
-// to a sweep over the bounding box, testing every stamp.
+// APPLY: every marked cell lies in the bounding box of the start cell and the end cells, which the mark phase left in
+// the scan's scratch slot, so the apply phase is a coalesced sweep of that box over the stamp plane (uint4 loads, four
+// in flight per thread; a scalar variant for levels whose rows are not 16-byte multiples): stamp == base+1 -> l += lf,
+// base+2 -> if (l < 50) l += lo, then P and the texture twin are rewritten.  One owner per cell by construction — no
+// atomics, deterministic.
 __device__ __forceinline__ void apply_cell(const HsbUpdateLevelDev& L, unsigned off, uint32_t v, float lf, float lo) {
   const uint32_t d = v - (L.stamp_base + 1u);
   if (d < 2u) {
@@ -392,7 +379,6 @@ __global__ void __launch_bounds__(256) update_apply_kernel(const __grid_constant
   if (P.gate_flag && *P.gate_flag == 0.0f) return;
   const int bx0 = cur[1], by0 = cur[2], bx1 = cur[3], by1 = cur[4];
   if (bx1 < bx0) return;                       // nothing was marked (pose outside the map, every beam dropped)
-  const unsigned count = (unsigned)cur[0];
   if (blockIdx.x == 0 && threadIdx.x == 0 && L.dirty) {   // both rectangles: replication [0..3] and host mirror [4..7]
     atomicMin(L.dirty + 0, bx0); atomicMin(L.dirty + 4, bx0);
     atomicMin(L.dirty + 1, by0); atomicMin(L.dirty + 5, by0);
@@ -401,25 +387,35 @@ __global__ void __launch_bounds__(256) update_apply_kernel(const __grid_constant
   }
   const float lf = P.log_odds_free, lo = P.log_odds_occ;
   const unsigned nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned rows = (unsigned)(by1 - by0 + 1);
   constexpr int U = 4;
-  if (count <= L.list_cap) {
-    for (unsigned base = tid; base < count; base += U * nthreads) {
+  if ((L.sx & 3) == 0) {   // rows are 16-byte aligned: four cells per load
+    const unsigned xa = (unsigned)bx0 & ~3u;
+    const unsigned w4 = (((unsigned)bx1 - xa) >> 2) + 1u;
+    const unsigned total = w4 * rows;
+    for (unsigned base = tid; base < total; base += U * nthreads) {
       unsigned off[U];
-      uint32_t v[U];
+      uint4 v[U];
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        const unsigned i = base + (unsigned)k * nthreads;
-        v[k] = L.stamp_base;
-        if (i < count) {
-          off[k] = __ldcg(L.list + i);
-          v[k] = __ldcg(L.stamp + off[k]);
+        const unsigned idx = base + (unsigned)k * nthreads;
+        v[k] = make_uint4(L.stamp_base, L.stamp_base, L.stamp_base, L.stamp_base);
+        if (idx < total) {
+          const unsigned r = idx / w4, c = idx - r * w4;
+          off[k] = ((unsigned)by0 + r) * (unsigned)L.sx + xa + 4u * c;
+          v[k] = __ldcg(reinterpret_cast<const uint4*>(L.stamp + off[k]));
         }
       }
 #pragma unroll
-      for (int k = 0; k < U; ++k) apply_cell(L, off[k], v[k], lf, lo);
+      for (int k = 0; k < U; ++k) {
+        apply_cell(L, off[k] + 0u, v[k].x, lf, lo);
+        apply_cell(L, off[k] + 1u, v[k].y, lf, lo);
+        apply_cell(L, off[k] + 2u, v[k].z, lf, lo);
+        apply_cell(L, off[k] + 3u, v[k].w, lf, lo);
+      }
     }
   } else {
-    const unsigned wd = (unsigned)(bx1 - bx0 + 1), rows = (unsigned)(by1 - by0 + 1);
+    const unsigned wd = (unsigned)(bx1 - bx0 + 1);
     const unsigned total = wd * rows;
     for (unsigned idx = tid; idx < total; idx += nthreads) {
       const unsigned rr = idx / wd, c = idx - rr * wd;
