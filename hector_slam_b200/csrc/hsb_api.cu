@@ -45,6 +45,7 @@ struct DevBuf {
 
 struct BatchSet {
   DevBuf hints, in, offsets, poses, cov, origo, tf;
+  cudaEvent_t chunk_ready[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t done[2] = {nullptr, nullptr};
   bool busy = false;
 };
@@ -92,7 +93,7 @@ struct hsb_handle {
   DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
   float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1, tune_auto_group = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1, tune_auto_group = 0, tune_stagger = 0;
   DevBuf d_trace;
   bool map_write_pending = false;   // a nowait SLAM step's map write may still be running on `stream`
   unsigned step_seq = 0;   // sequence number of the fused SLAM steps (host polling, hsb_slam_update_nowait)
@@ -282,6 +283,8 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st,
     if (groups > slots_staged && groups <= slots_plain)
       cap = may_split ? cap_for((groups + h->sm_count - 1) / h->sm_count) : 0;
   }
+  P.stagger_ns = h->tune_stagger;
+  P.sm_count = h->sm_count;
   P.prefetch = h->tune_prefetch;
   P.pace_slack = h->tune_pace > 0 ? h->tune_pace : P.pace_slack_req;
   P.pts_cap = cap;
@@ -391,11 +394,12 @@ int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
 // the end (3/8, 3/8, 3/16, 1/16 of the batch): the big early chunks run the kernel at full
 // efficiency (>= 1024 scans, profiles/r01_sweep_batches.log) and the exposed tail is a 1/16 chunk.
 // Returns the chunk boundaries (ascending, first 0, last B).
-// All chunks of one call use the launch shape of a B/8-scan batch (ShapeScope): the early chunks' kernels hide
-// under the next chunk's copy anyway, and the small exposed tail chunk gets several warps per scan.
+// All chunks of one call use ONE launch shape — that of a 3B/8-scan batch, the largest chunk (ShapeScope): most of a
+// call's kernel time is in the two large chunks, and with the copies on their own stream (submit_host_batch) the kernels
+// of a stream of calls run back to back, so their total must stay below the copy time of a call.
 struct ShapeScope {
   hsb_handle* h;
-  ShapeScope(hsb_handle* hh, int B, size_t nchunks) : h(hh) { h->shape_batch = nchunks > 1 ? std::max(1, B / 8) : 0; }
+  ShapeScope(hsb_handle* hh, int B, size_t nchunks) : h(hh) { h->shape_batch = nchunks > 1 ? std::max(1, (int)((long)B * 3 / 8)) : 0; }
   ~ShapeScope() { h->shape_batch = 0; }
 };
 std::vector<int> pipeline_bounds(int B, int fixed_chunk) {
@@ -536,8 +540,10 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
   for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking));
   for (int i = 0; i < 4; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
   for (int i = 0; i < 4; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->ev_sync[i], cudaEventDisableTiming));
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 2; ++k) {
     for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->bset[k].done[i], cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->bset[k].chunk_ready[i], cudaEventDisableTiming));
+  }
   for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaEventCreate(&h->ev_time[i]));
   HSB_CUDA_C(cudaMalloc(&h->d_dirty_all, HSB_MAX_LEVELS * 8 * sizeof(int)));
   HSB_CUDA_C(cudaHostAlloc(&h->h_pin, 64 * sizeof(float), cudaHostAllocMapped));
@@ -636,6 +642,8 @@ int hsb_destroy(hsb_handle* h) {
       if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i)
       if (S.done[i]) cudaEventDestroy(S.done[i]);
+    for (int i = 0; i < 8; ++i)
+      if (S.chunk_ready[i]) cudaEventDestroy(S.chunk_ready[i]);
   }
   if (h->d_dirty_all) cudaFree(h->d_dirty_all);
   for (int i = 0; i < 2; ++i)
@@ -737,6 +745,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "time_update")) h->tune_time_update = value;
   else if (!strcmp(key, "pdl")) h->tune_pdl = value;
   else if (!strcmp(key, "auto_group")) h->tune_auto_group = value;
+  else if (!strcmp(key, "stagger")) h->tune_stagger = value;
   else return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_tuning: unknown key '%s'", key);
   return HSB_OK;
 }
@@ -1083,16 +1092,18 @@ int submit_host_batch(hsb_handle* h, const HostBatch& hb, int* ticket) {
   const bool shared = hb.kind == IN_ENDPOINTS && !hb.offsets;
   if (shared) bounds = std::vector<int>{0, B};   // one shared scan: nothing big to overlap
   ShapeScope shape_scope(h, B, bounds.size() - 1);
-  cudaStream_t s0 = h->copy_stream[0];
+  // Stream roles: copy_stream[0] carries ALL host->device copies of all calls back to back, copy_stream[1] the kernels
+  // and the result copies; chunk c's kernel waits for chunk c's copy through an event.  (Round 1 alternated whole chunks
+  // between the two streams, so chunk c+2's copy queued behind chunk c's KERNEL and the copy engine idled — measured
+  // 430 us per 4096-scan call where the copies alone take 328 us.)
+  cudaStream_t s0 = h->copy_stream[0], s1 = h->copy_stream[1];
   if (hb.offsets) HSB_CUDA(h, cudaMemcpyAsync(d_off, hb.offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s0));
   if (shared && in_bytes > 0) HSB_CUDA(h, cudaMemcpyAsync(d_in, hb.in, in_bytes, cudaMemcpyHostToDevice, s0));
   HSB_CUDA(h, cudaMemcpyAsync(d_hints, hb.hints, (size_t)B * 12, cudaMemcpyHostToDevice, s0));
   if (d_tf) HSB_CUDA(h, cudaMemcpyAsync(d_tf, hb.transforms, (size_t)B * 12 * sizeof(double), cudaMemcpyHostToDevice, s0));
-  HSB_CUDA(h, cudaEventRecord(h->ev[0], s0));
-  HSB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[1], h->ev[0], 0));
   for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
     const int b0 = bounds[ci], b1 = bounds[ci + 1];
-    cudaStream_t st = h->copy_stream[ci & 1];
+    cudaStream_t st = s1;
     if (!shared) {
       size_t p0, p1;
       if (hb.kind == IN_RANGES) {
@@ -1103,8 +1114,11 @@ int submit_host_batch(hsb_handle* h, const HostBatch& hb, int* ticket) {
         p1 = (size_t)hb.offsets[b1] * unit;
       }
       if (p1 > p0)
-        HSB_CUDA(h, cudaMemcpyAsync(d_in + p0, reinterpret_cast<const char*>(hb.in) + p0, p1 - p0, cudaMemcpyHostToDevice, st));
+        HSB_CUDA(h, cudaMemcpyAsync(d_in + p0, reinterpret_cast<const char*>(hb.in) + p0, p1 - p0, cudaMemcpyHostToDevice, s0));
     }
+    cudaEvent_t ready = S.chunk_ready[ci < 8 ? ci : 7];
+    HSB_CUDA(h, cudaEventRecord(ready, s0));           // hints / offsets / this chunk's input are on the device
+    HSB_CUDA(h, cudaStreamWaitEvent(s1, ready, 0));
     float* o_pose = d_poses + 3 * (size_t)b0;
     float* o_cov = d_cov ? d_cov + 9 * (size_t)b0 : nullptr;
     if (hb.kind == IN_RANGES)

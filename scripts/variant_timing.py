@@ -13,12 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    "r01-like (waterfall, +1.0 coords, branchy acc)": ["-DHSB_UNIFORM_HANDLE=0", "-DHSB_TLD4_OFFSET=0", "-DHSB_PRED_ACC=0"],
     "uniform handle only": ["-DHSB_UNIFORM_HANDLE=1", "-DHSB_TLD4_OFFSET=0", "-DHSB_PRED_ACC=0"],
     "uniform + TLD4.AOFFI": ["-DHSB_UNIFORM_HANDLE=1", "-DHSB_TLD4_OFFSET=1", "-DHSB_PRED_ACC=0"],
     "uniform + predicated acc": ["-DHSB_UNIFORM_HANDLE=1", "-DHSB_TLD4_OFFSET=0", "-DHSB_PRED_ACC=1"],
     "uniform + AOFFI + predicated (all)": ["-DHSB_UNIFORM_HANDLE=1", "-DHSB_TLD4_OFFSET=1", "-DHSB_PRED_ACC=1"],
-    "AOFFI + predicated, waterfall kept": ["-DHSB_UNIFORM_HANDLE=0", "-DHSB_TLD4_OFFSET=1", "-DHSB_PRED_ACC=1"],
 }
 
 
@@ -43,11 +41,18 @@ def run(name):
         d_h = torch.from_numpy(h).to(dev)
         d_o = torch.from_numpy(o).to(dev)
         d_p = torch.empty((B, 3), dtype=torch.float32, device=dev)
-        configs = [("G=1 unstaged", dict(stage_smem=0)), ("G=1 staged prefix", dict(stage_smem=1, partial=1)),
-                   ("G=28 unstaged", dict(warps_per_scan=1, scans_per_block=28, stage_smem=0))] if B == 4096 else \
-                  [("G=1 staged", dict(stage_smem=2)), ("G=1 unstaged", dict(stage_smem=0))]
+        if B == 4096:
+            configs = [("G=1 unstaged", dict(stage_smem=0)), ("G=1 staged prefix", dict(stage_smem=1, partial=1))]
+            for st in (0, 100, 200, 350, 700):
+                configs.append((f"G=28 unstaged stagger={st}", dict(warps_per_scan=1, scans_per_block=28, stage_smem=0, stagger=st)))
+                configs.append((f"G=28 prefix   stagger={st}", dict(warps_per_scan=1, scans_per_block=28, stage_smem=1, partial=1, stagger=st)))
+            for st in (200, 350):
+                configs.append((f"G=1 unstaged stagger={st}", dict(stage_smem=0, stagger=st)))
+                configs.append((f"G=1 prefix   stagger={st}", dict(stage_smem=1, partial=1, stagger=st)))
+        else:
+            configs = [("G=1 staged", dict(stage_smem=2)), ("G=1 unstaged", dict(stage_smem=0))]
         for cname, kw in configs:
-            rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=1, partial=0, pace=0, auto_group=0)
+            rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=1, partial=0, pace=0, auto_group=0, stagger=0)
             rep.set_tuning(**kw)
 
             def go(i):
@@ -57,19 +62,19 @@ def run(name):
                 go(i)
             torch.cuda.synchronize()
             best = 1e9
-            for r in range(3):
+            for r in range(5):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                iters = 20 if B == 4096 else 5
+                iters = 30 if B == 4096 else 5
                 for i in range(iters):
                     go(i)
                 e1.record()
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) / iters)
-            out.append(f"B={B:5d} {cname:18s} {best * 1e3:8.1f} us {B / best / 1e3:6.2f} M/s")
+            out.append(f"B={B:5d} {cname:28s} {best * 1e3:8.1f} us {B / best / 1e3:6.2f} M/s")
     # single-scan latency of the fused step (sync) on this map
     sc = [np.ascontiguousarray(pts[offs[i]:offs[i + 1]]) for i in range(32)]
-    rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=1, partial=0)
+    rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=1, partial=0, stagger=0)
     rep.setMapUpdateMinDistDiff(0.0)
     rep.setMapUpdateMinAngleDiff(0.0)
     import time
