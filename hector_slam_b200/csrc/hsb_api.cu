@@ -93,7 +93,7 @@ struct hsb_handle {
   DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
   float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1, tune_auto_group = 0, tune_stagger = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1, tune_auto_group = 1, tune_stagger = 0;
   DevBuf d_trace;
   bool map_write_pending = false;   // a nowait SLAM step's map write may still be running on `stream`
   unsigned step_seq = 0;   // sequence number of the fused SLAM steps (host polling, hsb_slam_update_nowait)
@@ -286,7 +286,7 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st,
   P.stagger_ns = h->tune_stagger;
   P.sm_count = h->sm_count;
   P.prefetch = h->tune_prefetch;
-  P.pace_slack = h->tune_pace > 0 ? h->tune_pace : P.pace_slack_req;
+  P.pace_slack = h->tune_pace;
   P.pts_cap = cap;
   size_t smem = header + (size_t)Gr * cap * 8;
   if (smem > 48 * 1024) {
@@ -373,15 +373,17 @@ int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   int Gr = 0;   // 0: as many groups per CTA as the instantiation has
   if (G <= 0) {
     G = 1;
-    // One-wave batches of one-warp scans (tuning "auto_group"): ONE CTA per SM holding ceil(B / SMs) <= 28 scans, paced
-    // (match_kernel.cuh) — all scans of an SM advance together and end together instead of trailing off over the last
-    // third of the launch (profiles/r02_k1_timeline.md).  Larger batches keep one scan per CTA: finished warps are
-    // replaced at once there and a CTA-wide drain would cost more than the tail it removes.
+    // One-wave batches of one-warp scans (tuning "auto_group", on by default): ONE CTA per SM holding ceil(B / SMs) <= 28
+    // scans instead of 28 one-warp CTAs.  Measured at B = 4096 (profiles/r02_k1_variants.log): 137 us against 145 us —
+    // one CTA pays the 1 KB per-CTA shared-memory reservation once, so almost the whole scan (1024 of 1081 endpoints)
+    // can be staged at full residency, and its warps start and end together (per-scan end times within 130-140 us
+    // instead of 122-153 us).  Larger batches keep one scan per CTA: finished warps are replaced at once there, which
+    // a CTA-wide drain would prevent.
     const long Bs = h->shape_batch > 0 ? h->shape_batch : P.B;
-    if (h->tune_auto_group && W == 1 && !P.ranges && !P.cloud && Bs == P.B && Bs <= (long)h->sm_count * 28) {
+    if (h->tune_auto_group && W == 1 && !P.ranges && !P.cloud && Bs == P.B && Bs <= (long)h->sm_count * 28 &&
+        (h->tune_unroll == 0 || h->tune_unroll == 4)) {
       G = 28;
       Gr = (int)((Bs + h->sm_count - 1) / h->sm_count);
-      if (P.pace_slack_req == 0) P.pace_slack_req = h->tune_auto_group;
     }
   }
   int U = h->tune_unroll > 0 ? h->tune_unroll : 4;

@@ -57,7 +57,6 @@ struct HsbMatchParams {
   unsigned seq_value;       // covariance of the step are visible to the host — the host may poll it instead of synchronising
   int stagger_ns;           // > 0: the warps sharing an SM start this many ns apart (see match_kernel: phase-locking)
   int sm_count;             // SMs of the device (the one-scan-per-CTA shapes derive a warp's rank on its SM from blockIdx)
-  int pace_slack_req;       // host-side scratch: pacing slack the auto-launcher asks for (copied into pace_slack)
   int pace_slack;           // > 0: groups of a CTA keep within this many evaluations of the slowest one (see match_kernel)
   int prefetch;             // != 0: L2 bulk prefetch of the part of a scan that is read from global memory
   // diagnostics (hsb_set_tuning "trace"): per scan 8 x u64 = {start, after coarsest level, ..., end (slot 1+levels), -, smid (slot 7)}

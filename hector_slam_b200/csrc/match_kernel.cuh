@@ -144,9 +144,12 @@ __device__ __forceinline__ void solve3(const Acc& s, float& o0, float& o1, float
 #define HSB_TLD4_OFFSET 1
 #endif
 // 1: the nine H / dTr accumulations of an endpoint are predicated on "inside the map" (PTX @p fma) instead of sitting in
-//    a branch (BSSY / BRA / BSYNC per endpoint); out-of-map endpoints are rare, so nothing is gained by skipping them.
+//    a branch (BSSY / BRA / BSYNC per endpoint): 3 instructions per endpoint fewer, bit-identical — and NOT faster: measured
+//    (profiles/r02_k1_variants.log) 32.7 vs 34.3 M matches/s at 65 536 scans per launch, equal at 4096.  The kernel is
+//    bound by the texture pipe, and the branchy form consumes the gathers one by one as they return (DEPBAR per
+//    endpoint) where the predicated form waits for them in pairs.  Off.
 #ifndef HSB_PRED_ACC
-#define HSB_PRED_ACC 1
+#define HSB_PRED_ACC 0
 #endif
 
 struct PointPre {

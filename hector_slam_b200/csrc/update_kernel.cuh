@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
     }
     if (tlane == 0) atomicMax(L.stamp + (unsigned)y1 * (unsigned)L.sx + (unsigned)x1, occ_s);   // bresenhamCellOcc :226-241, :211-212
   }
-  // bounding box of this warp's beams (+ the common start cell) -> scratch slot, 4 atomics per warp
+  // bounding box of this CTA's beams (+ the common start cell) -> scratch slot.  One reduction per CTA and only the
+  // atomics that can still enlarge the box: with 4 atomics per WARP (6500 warps on the same four words) the drain of the
+  // same-address atomics alone cost ~7 us of a 17 us kernel (profiles/r02_slam_step_launches.md).
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
@@ -334,11 +336,22 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
     bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
     by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
   }
-  if ((threadIdx.x & 31) == 0 && bx1 >= 0) {
-    atomicMin(slot + 1, min(bx0, f.x0));
-    atomicMin(slot + 2, min(by0, f.y0));
-    atomicMax(slot + 3, max(bx1, f.x0));
-    atomicMax(slot + 4, max(by1, f.y0));
+  __shared__ int box[4][8];
+  const int wi = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { box[0][wi] = bx0; box[1][wi] = by0; box[2][wi] = bx1; box[3][wi] = by1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      bx0 = min(bx0, box[0][k]); by0 = min(by0, box[1][k]); bx1 = max(bx1, box[2][k]); by1 = max(by1, box[3][k]);
+    }
+    if (bx1 >= 0) {
+      bx0 = min(bx0, f.x0); by0 = min(by0, f.y0); bx1 = max(bx1, f.x0); by1 = max(by1, f.y0);
+      const volatile int* cur = slot;
+      if (bx0 < cur[1]) atomicMin(slot + 1, bx0);
+      if (by0 < cur[2]) atomicMin(slot + 2, by0);
+      if (bx1 > cur[3]) atomicMax(slot + 3, bx1);
+      if (by1 > cur[4]) atomicMax(slot + 4, by1);
+    }
   }
 }
 

@@ -52,14 +52,12 @@ def timed(iters=20):
 
 base = dict(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=0, prefetch=0, trace=0, seq=0, pace=0, auto_group=0)
 variants = [
-    ("default", {}),
+    ("G=1 unstaged (round-1 shape)", {}),
     ("G=1 partial staging", dict(partial=1)),
+    ("auto (grouped, staged prefix)", dict(auto_group=1, partial=1)),
 ]
-for ag in (1, 2, 3):
-    variants.append((f"auto_group pace={ag} staged prefix", dict(auto_group=ag, partial=1)))
-    variants.append((f"auto_group pace={ag} unstaged", dict(auto_group=ag, stage_smem=0)))
-for G in (28, 14, 7, 2):
-    for pace in (0, 1, 2, 4):
+for G in (28, 14):
+    for pace in (0, 1):
         for stage, part in ((0, 0), (1, 1)):
             variants.append((f"G={G} pace={pace} " + ("staged prefix" if stage else "unstaged"),
                              dict(warps_per_scan=1, scans_per_block=G, pace=pace, stage_smem=stage, partial=part)))
@@ -145,9 +143,8 @@ if B > 8192:
     rep.set_tuning(**base)
     rep.close()
     sys.exit(0)
-timeline("default (G=1 unstaged)", {})
+timeline("G=1 unstaged (round-1 shape)", {})
 slot_study()
-timeline("G=28 pace=1 staged prefix", dict(warps_per_scan=1, scans_per_block=28, pace=1, stage_smem=1, partial=1))
-timeline("G=28 pace=0 staged prefix", dict(warps_per_scan=1, scans_per_block=28, pace=0, stage_smem=1, partial=1))
+timeline("auto (grouped, staged prefix)", dict(auto_group=1, partial=1))
 rep.set_tuning(**base)
 rep.close()

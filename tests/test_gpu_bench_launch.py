@@ -51,7 +51,8 @@ def device_match(rep, w, n, **tuning):
     import torch
 
     dev = torch.device("cuda", 0)
-    rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=1, prefetch=0)
+    rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=1, prefetch=0, auto_group=1, pace=0,
+                   stagger=0)
     rep.set_tuning(**tuning)
     d_pts = torch.from_numpy(w["pts"][: w["offs"][n]]).to(dev)
     d_hints = torch.from_numpy(w["hints"][:n]).to(dev)
@@ -65,31 +66,34 @@ def device_match(rep, w, n, **tuning):
 
 
 def test_value_launch_all_4096(workload):
-    """bench.py `value`: hsb_match_batch_device, B = 4096, auto shape."""
+    """bench.py `value`: hsb_match_batch_device, B = 4096, auto shape = one CTA of 28 one-warp scans per SM."""
     w = workload
     got, cov, shape = device_match(w["rep"], w, w["B"])
-    print("launch shape:", shape)
-    assert shape["warps_per_scan"] == 1 and shape["scans_per_block"] == 1 and shape["grid"] == 4096
+    report(f"value launch shape: {shape}")
+    assert shape["warps_per_scan"] == 1 and shape["scans_per_block"] == 28 and shape["grid"] == 147
     compare(got, w, w["B"], "value launch")
     ok = w["ok"]
     scale = np.abs(w["want_cov"][ok]).max(axis=(1, 2))
     assert (np.abs(cov[ok].reshape(-1, 3, 3) - w["want_cov"][ok]).max(axis=(1, 2)) <= 2e-3 * scale).all()
-    # the round-1 launch (nothing staged at one wave) and the fully staged one give the same bits: staging
-    # does not change which lane sums which endpoint in which order
-    got0, _, shape0 = device_match(w["rep"], w, w["B"], partial=0)
-    assert shape0["staged_points"] == 0
-    got2, _, shape2 = device_match(w["rep"], w, w["B"], stage_smem=2)
+    # one scan per CTA (the shape of larger batches), with nothing / a prefix / everything staged in shared memory, with
+    # the L2 prefetch, paced, staggered: which lane sums which endpoint in which order never changes -> the same bits
+    got0, _, shape0 = device_match(w["rep"], w, w["B"], auto_group=0, partial=0)
+    assert shape0["staged_points"] == 0 and shape0["scans_per_block"] == 1 and shape0["grid"] == 4096
+    got1, _, shape1 = device_match(w["rep"], w, w["B"], auto_group=0, partial=1)
+    assert 0 < shape1["staged_points"] < 1081
+    got2, _, shape2 = device_match(w["rep"], w, w["B"], auto_group=0, stage_smem=2)
     assert shape2["staged_points"] == 1081
-    assert np.array_equal(got, got0) and np.array_equal(got, got2)
-    gotp, _, _ = device_match(w["rep"], w, w["B"], prefetch=1)
-    assert np.array_equal(got, gotp)
+    assert np.array_equal(got, got0) and np.array_equal(got, got1) and np.array_equal(got, got2)
+    for kw in (dict(prefetch=1), dict(pace=1), dict(stagger=150), dict(stage_smem=0)):
+        gotv, _, _ = device_match(w["rep"], w, w["B"], **kw)
+        assert np.array_equal(got, gotv), kw
 
 
-@pytest.mark.parametrize("n,warps", [(256, 8), (512, 4), (1024, 2), (2048, 1), (3000, 1)])
-def test_every_auto_shape(workload, n, warps):
+@pytest.mark.parametrize("n,warps,groups", [(256, 8, 1), (512, 4, 1), (1024, 2, 1), (2048, 1, 14), (3000, 1, 21)])
+def test_every_auto_shape(workload, n, warps, groups):
     w = workload
     got, _, shape = device_match(w["rep"], w, n)
-    assert shape["warps_per_scan"] == warps, shape
+    assert shape["warps_per_scan"] == warps and shape["scans_per_block"] == groups, shape
     compare(got, w, n, f"B={n} auto shape {shape}")
 
 
