@@ -7,8 +7,8 @@ mkdir -p $out
 export PYTHONUNBUFFERED=1
 echo "== pytest (full gpu suite)"; timeout 900 python -m pytest tests -m gpu -q > $out/${tag}_pytest.log 2>&1; tail -3 $out/${tag}_pytest.log
 echo "== k1 probe"; timeout 300 python scripts/k1_probe.py 4096 > $out/${tag}_k1_probe.log 2>&1; head -60 $out/${tag}_k1_probe.log
-timeout 300 python scripts/k1_probe.py 3000 > $out/${tag}_k1_probe_b3000.log 2>&1; head -12 $out/${tag}_k1_probe_b3000.log
 timeout 300 python scripts/k1_probe.py 65536 > $out/${tag}_k1_probe_b65536.log 2>&1; head -4 $out/${tag}_k1_probe_b65536.log
-echo "== A/B: instruction-level variants must not change a bit"; timeout 600 python scripts/alt_compare.py > $out/${tag}_alt_compare.log 2>&1; tail -25 $out/${tag}_alt_compare.log
+echo "== single-scan step, gather batch 4 vs 5"; for u in 4 5; do timeout 300 python bench.py --only slam --no-cpu-baseline --tune unroll=$u > $out/${tag}_slam_u$u.json 2>> $out/${tag}_bench.err; python -c "
+import json,sys; d=json.load(open('$out/${tag}_slam_u$u.json')); c=d['config3_slam_step']; print('unroll $u:', {k:round(v,1) for k,v in c.items() if isinstance(v,float)}, 'k2_ms', d['roofline_k2']['kernel_ms'])"; done
 echo "== bench N=1"; timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 600 $out/${tag}_bench.err; head -c 1500 $out/${tag}_bench.json
 echo "== reference arm"; timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err
