@@ -380,7 +380,7 @@ int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
     // instead of 122-153 us).  Larger batches keep one scan per CTA: finished warps are replaced at once there, which
     // a CTA-wide drain would prevent.
     const long Bs = h->shape_batch > 0 ? h->shape_batch : P.B;
-    if (h->tune_auto_group && W == 1 && !P.ranges && !P.cloud && Bs == P.B && Bs <= (long)h->sm_count * 28 &&
+    if (h->tune_auto_group && W == 1 && !P.ranges && !P.cloud && std::max<long>(Bs, P.B) <= (long)h->sm_count * 28 &&
         (h->tune_unroll == 0 || h->tune_unroll == 4)) {
       G = 28;
       Gr = (int)((Bs + h->sm_count - 1) / h->sm_count);
@@ -391,17 +391,17 @@ int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G, U, Gr);
 }
 
-// Copy/compute pipeline of the host-buffer batch calls: chunk c's host->device copy overlaps the
-// match kernel of chunk c-1; only the LAST chunk's kernel is exposed.  So the chunks shrink towards
-// the end (3/8, 3/8, 3/16, 1/16 of the batch): the big early chunks run the kernel at full
-// efficiency (>= 1024 scans, profiles/r01_sweep_batches.log) and the exposed tail is a 1/16 chunk.
-// Returns the chunk boundaries (ascending, first 0, last B).
-// All chunks of one call use ONE launch shape — that of a 3B/8-scan batch, the largest chunk (ShapeScope): most of a
-// call's kernel time is in the two large chunks, and with the copies on their own stream (submit_host_batch) the kernels
-// of a stream of calls run back to back, so their total must stay below the copy time of a call.
+// Copy/compute pipeline of the host-buffer batch calls.  A call of >= 2048 scans travels in TWO halves: the second
+// half's host->device copy overlaps the first half's kernel, and — with the submit / wait form — the next call's copies
+// overlap this call's second kernel, so a stream of batches is bound by the PCIe copy of its inputs.  (Round 1 cut a call
+// into four shrinking chunks to shorten the exposed tail of a single blocking call.  Measured in round 2: every chunk
+// kernel costs at least one scan latency, 40-75 us with several warps per scan, whatever its size, so four small launches
+// took 400-450 us where one large launch takes 140 us — the kernels, not the 326 us of copies, bounded the call.)
+// Both halves use ONE launch shape, that of a B/2-scan batch (ShapeScope): a scan's result must not depend on the half
+// it travels in, so that results are invariant under a permutation of the batch, as the reference's are.
 struct ShapeScope {
   hsb_handle* h;
-  ShapeScope(hsb_handle* hh, int B, size_t nchunks) : h(hh) { h->shape_batch = nchunks > 1 ? std::max(1, (int)((long)B * 3 / 8)) : 0; }
+  ShapeScope(hsb_handle* hh, int B, size_t nchunks) : h(hh) { h->shape_batch = nchunks > 1 ? std::max(1, B / (int)nchunks) : 0; }
   ~ShapeScope() { h->shape_batch = 0; }
 };
 std::vector<int> pipeline_bounds(int B, int fixed_chunk) {
@@ -409,14 +409,8 @@ std::vector<int> pipeline_bounds(int B, int fixed_chunk) {
   b.push_back(0);
   if (fixed_chunk > 0) {
     for (int x = fixed_chunk; x < B; x += fixed_chunk) b.push_back(x);
-  } else if (B >= 4096) {
-    const int a = (int)((long)B * 3 / 8), c = (int)((long)B * 3 / 16);
-    b.push_back(a);
-    b.push_back(2 * a);
-    b.push_back(2 * a + c);
   } else if (B >= 2048) {
     b.push_back(B / 2);
-    b.push_back(B / 2 + B / 4);
   }
   b.push_back(B);
   return b;
@@ -1095,9 +1089,8 @@ int submit_host_batch(hsb_handle* h, const HostBatch& hb, int* ticket) {
   if (shared) bounds = std::vector<int>{0, B};   // one shared scan: nothing big to overlap
   ShapeScope shape_scope(h, B, bounds.size() - 1);
   // Stream roles: copy_stream[0] carries ALL host->device copies of all calls back to back, copy_stream[1] the kernels
-  // and the result copies; chunk c's kernel waits for chunk c's copy through an event.  (Round 1 alternated whole chunks
-  // between the two streams, so chunk c+2's copy queued behind chunk c's KERNEL and the copy engine idled — measured
-  // 430 us per 4096-scan call where the copies alone take 328 us.)
+  // and the result copies; a chunk's kernel waits for its copy through an event, so the copy engine never queues behind
+  // a kernel.
   cudaStream_t s0 = h->copy_stream[0], s1 = h->copy_stream[1];
   if (hb.offsets) HSB_CUDA(h, cudaMemcpyAsync(d_off, hb.offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s0));
   if (shared && in_bytes > 0) HSB_CUDA(h, cudaMemcpyAsync(d_in, hb.in, in_bytes, cudaMemcpyHostToDevice, s0));

@@ -2,7 +2,7 @@
 oracle/_ref is present) at the benchmark's own size.
 
 VERDICT r01 weak #1: `value` runs hsb_match_batch_device at B = 4096 with the auto-selected shape (one warp per scan,
-endpoints partly staged / read through L1), `e2e` runs the pipelined host calls (shape of a 3B/8 batch, the largest chunk) — every one of
+endpoints partly staged / read through L1), `e2e` runs the pipelined host calls (two halves, shape of a B/2 batch) — every one of
 these, and every other shape the auto-launcher can pick (B = 256 .. 4096 -> 8, 4, 2, 1 warps per scan), is checked
 here on ALL scans of the batch, not on a golden subset.  The workload is bench.py's (same generator, same seeds).
 """
@@ -107,7 +107,8 @@ def test_deeper_gather_batches(workload, unroll):
 
 def test_e2e_launches_all_4096(workload):
     """bench.py `e2e` (hsb_match_batch_ranges) and `e2e_endpoints` (hsb_match_batch): pinned host buffers, chunked
-    copy/compute pipeline, all chunks with the launch shape of a 3B/8 batch (the largest chunk)."""
+    copy/compute
+    pipeline in two halves, both with the launch shape of a B/2 batch."""
     import torch
 
     from hector_slam_b200 import synth
@@ -119,7 +120,7 @@ def test_e2e_launches_all_4096(workload):
     h_pts = torch.from_numpy(w["pts"]).pin_memory()
     h_hints = torch.from_numpy(w["hints"]).pin_memory()
     got, _ = rep.match_batch(h_hints, h_pts, w["offs"])
-    assert rep.last_launch_shape()["warps_per_scan"] == 2   # every chunk of a 4096-scan call: shape of a 1536-scan batch
+    assert rep.last_launch_shape()["warps_per_scan"] == 1   # both halves of a 4096-scan call: shape of a 2048-scan batch
     compare(np.asarray(got), w, B, "e2e_endpoints (hsb_match_batch)")
     rep.set_scan_format(**synth.SCAN_FORMAT)
     h_ranges = torch.from_numpy(w["ranges"]).pin_memory()
