@@ -27,6 +27,14 @@ def workload(hsb_lib, pyoracle, oracle_kinds):
     orc.set_update_factors(0.4, 0.9)
     pyoracle.build_map_known_poses(orc, world)
     want, want_cov, _ = orc.match_batch(hints, pts, offs, nthreads=16)
+    # the same batch as the NODE would see it: endpoints converted from the raw ranges by the reference's own converter
+    # (bench.py's endpoint arrays come from numpy's cos / sin, which differ from glibc's cosf / sinf in the last bit)
+    from hector_slam_b200 import synth
+    f = synth.SCAN_FORMAT
+    conv = [pyoracle.scan_to_points(ranges[b], f["angle_min"], f["angle_increment"], f["range_min"], f["range_max"], 20.0,
+                                    kind=kind) for b in range(B)]
+    r_offs = np.concatenate([[0], np.cumsum([c.shape[0] for c in conv])]).astype(np.int32)
+    want_r, _, _ = orc.match_batch(hints, np.concatenate(conv), r_offs, nthreads=16)
     rep = capi.MapRepB200(bench.RES, bench.MAP_SIZE, levels=bench.LEVELS, update_factor_free=0.4,
                           update_factor_occupied=0.9)
     for l in range(bench.LEVELS):
@@ -36,13 +44,13 @@ def workload(hsb_lib, pyoracle, oracle_kinds):
     ok = np.abs(want[:, :2] - hints[:, :2]).max(axis=1) < 0.5
     assert ok.mean() > 0.98, ok.mean()
     yield dict(kind=kind, B=B, pts=pts, offs=offs, hints=hints, ranges=ranges, want=want, want_cov=want_cov, ok=ok,
-               rep=rep, poses=poses)
+               rep=rep, poses=poses, want_ranges=want_r)
     rep.close()
 
 
-def compare(got, w, n, what):
+def compare(got, w, n, what, key="want"):
     ok = w["ok"][:n]
-    ex, ey, ea = pose_err(got[ok], w["want"][:n][ok])
+    ex, ey, ea = pose_err(got[ok], w[key][:n][ok])
     report(f"{what}: {int(ok.sum())} of {n} scans compared with the {w['kind']} oracle, max diff x {ex:.2e} y {ey:.2e} psi {ea:.2e}")
     assert max(ex, ey) <= 1e-4 and ea <= 1e-4, (what, ex, ey, ea)
 
@@ -125,7 +133,7 @@ def test_e2e_launches_all_4096(workload):
     rep.set_scan_format(**synth.SCAN_FORMAT)
     h_ranges = torch.from_numpy(w["ranges"]).pin_memory()
     got_r, _ = rep.match_batch_ranges(h_hints, h_ranges)
-    compare(np.asarray(got_r), w, B, "e2e (hsb_match_batch_ranges)")
+    compare(np.asarray(got_r), w, B, "e2e (hsb_match_batch_ranges)", key="want_ranges")
     # a second call reuses the staging buffers (double-buffered across calls): same answer
     got_r2, _ = rep.match_batch_ranges(h_hints, h_ranges)
     assert np.array_equal(np.asarray(got_r), np.asarray(got_r2))
@@ -137,7 +145,7 @@ def test_e2e_launches_all_4096(workload):
                                   torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert rep.last_launch_shape()["warps_per_scan"] == 1
-    compare(d_p.cpu().numpy(), w, B, "ranges on the device, auto shape")
+    compare(d_p.cpu().numpy(), w, B, "ranges on the device, auto shape", key="want_ranges")
 
 
 def test_submit_wait_pipeline_equals_blocking_calls(workload):
