@@ -403,6 +403,13 @@ def main():
     world, poses, pts, offs, hints = make_workload(rank, args.batch)
     ranges = np.ascontiguousarray(make_workload.ranges)
     B = args.batch
+    # endpoints exactly as the node's converter produces them from these ranges (make_workload's come from numpy's cos / sin,
+    # which differ from glibc's cosf / sinf in the last bit): the device-resident path and the host paths then see
+    # identical scans and `e2e.max_abs_diff_vs_device_path` is a true consistency check
+    rep.set_scan_format(**synth.SCAN_FORMAT)
+    conv = [rep.scan_to_points(ranges[b]) for b in range(B)]
+    if all(c.shape[0] == N_PTS for c in conv):
+        pts = np.ascontiguousarray(np.concatenate(conv), dtype=np.float32)
 
     # ---- map: built once on rank 0 through the product path, replicated with one NCCL broadcast
     if rank == 0:
