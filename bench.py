@@ -303,17 +303,17 @@ def time_device_steps(torch, dist, world_size, dev, fn, steps, warmup):
     torch.cuda.synchronize()
     if world_size > 1:
         dist.barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    e0.record()                      # ONE event pair around the K steps: per-step events would sit between the launches
     for i in range(steps):
-        ev[i][0].record()
         fn(warmup + i)
-        ev[i][1].record()
+    e1.record()
     torch.cuda.synchronize()
     if world_size > 1:
         dist.barrier()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    span_ms = ev[0][0].elapsed_time(ev[-1][1])
+    span_ms = e0.elapsed_time(e1)
+    step_ms = [span_ms / steps] * steps
     t = torch.tensor([span_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
