@@ -9,7 +9,7 @@ export PYTHONUNBUFFERED=1
 nvidia-smi -L > $out/${tag}_gpus.txt
 echo "== 2-GPU NCCL tile broadcast test"
 timeout 600 python -m pytest tests/test_gpu_tiles.py -q > $out/${tag}_pytest_tiles.log 2>&1; tail -3 $out/${tag}_pytest_tiles.log
-for n in 1 $N; do
+for n in ${NLIST:-1 $N}; do
   echo "== bench N=$n"
   if [ $n -eq 1 ]; then
     timeout 900 python bench.py --gpus 1 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
