@@ -753,6 +753,8 @@ def extra_config5(torch, dist, capi, synth, parallel, new_rep, rank, world_size,
         rep.setMapUpdateMinDistDiff(0.0)
         rep.setMapUpdateMinAngleDiff(0.0)
         stats, bc_us, cells = {}, [], []
+        tbuf = parallel.tile_buffer(dev)
+        one_shot = [True]
 
         def replay_step(i):
             match(i)
@@ -760,24 +762,39 @@ def extra_config5(torch, dist, capi, synth, parallel, new_rep, rank, world_size,
                 torch.cuda.current_stream().synchronize()   # the owner's map write must not overtake its own match
                 rep.slam_update(whints[i % 16], wscans[i % 16])
             t0 = time.perf_counter()
-            parallel.broadcast_dirty_tiles(rep, dev, src=0, stats=stats)
+            if one_shot[0]:
+                parallel.broadcast_dirty_tiles_async(rep, tbuf, src=0)
+            else:
+                parallel.broadcast_dirty_tiles(rep, dev, src=0, stats=stats)
             if i >= 3:
                 bc_us.append((time.perf_counter() - t0) * 1e6)
                 cells.append(stats.get("cells", 0))
 
         rp_steps, rp_warm = 10, 3
-        for i in range(rp_warm):
-            replay_step(i)
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(rp_steps):
-            replay_step(rp_warm + i)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-        dist.barrier()
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+
+        def timed_replay():
+            for i in range(rp_warm):
+                replay_step(i)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for i in range(rp_steps):
+                replay_step(rp_warm + i)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+            dist.barrier()
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return te
+
+        one_shot[0] = False
+        te2 = timed_replay()                 # two-step protocol (sizes through the hosts)
+        two_step_us, two_step_cells = float(np.median(bc_us)), float(np.median(cells))
+        bc_us.clear()
+        cells.clear()
+        one_shot[0] = True
+        te = timed_replay()                  # one-shot protocol (self-describing buffer)
+        overflows = rep.replication_overflows()
         # replicas bit-identical to the owner: checksum of every plane
         sums = torch.stack([parallel.level_plane_tensor(rep, l, dev).double().sum() for l in range(LEVELS)])
         allsums = [torch.empty_like(sums) for _ in range(world_size)]
@@ -786,14 +803,17 @@ def extra_config5(torch, dist, capi, synth, parallel, new_rep, rank, world_size,
         out["replay_with_tile_broadcast"] = {
             "value": world_size * B * rp_steps / float(te.item()), "unit": "scan-matches/s (wall clock, map write + NCCL tile "
             "broadcast every step inside the timed region)", "steps": rp_steps, "ms_per_step": 1e3 * float(te.item()) / rp_steps,
-            "broadcast_us_p50": float(np.median(bc_us)), "cells_per_broadcast_p50": float(np.median(cells)),
-            "bytes_per_broadcast_p50": float(np.median(cells)) * 4 + 16 * LEVELS,
-            "collectives_per_step": "2 x ncclBroadcast (rectangles of all levels; one packed buffer of all levels' rows)",
+            "protocol": "one-shot: device-side pack of all levels' dirty rectangles + their descriptions into a fixed "
+                        f"{tbuf.numel() * 4 >> 20} MB buffer, ONE ncclBroadcast, device-side unpack; no host round trip",
+            "host_us_per_broadcast_p50": float(np.median(bc_us)), "overflows": int(overflows),
             "replicas_bit_identical": bool(same),
-            "limiter": "host-synchronous protocol: the rectangle sizes must reach every host before the payload buffer "
-                       "can be sized (one device->host copy + two broadcast launches), ~100 us per step against a "
-                       "~150 us match step"}
-        assert same, "replica planes differ from the owner's after tile broadcasts"
+            "two_step_protocol": {"value": world_size * B * rp_steps / float(te2.item()),
+                                  "ms_per_step": 1e3 * float(te2.item()) / rp_steps, "broadcast_us_p50": two_step_us,
+                                  "cells_per_broadcast_p50": two_step_cells,
+                                  "bytes_per_broadcast_p50": two_step_cells * 4 + 16 * LEVELS,
+                                  "collectives_per_step": "2 x ncclBroadcast (rectangles, then one packed buffer of all "
+                                                          "levels' rows sized from them on every host)"}}
+        assert same and overflows == 0, "replica planes differ from the owner's after tile broadcasts"
     rep.close()
     return {"config5_replay_8192": out}
 

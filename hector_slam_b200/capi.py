@@ -32,7 +32,7 @@ EXPORTED = [
     "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device", "hsb_raycast_batch",
     "hsb_read_trace", "hsb_get_last_launch_shape", "hsb_get_last_update_device_ms",
     "hsb_match_batch_submit", "hsb_match_batch_ranges_submit", "hsb_match_batch_cloud_submit", "hsb_match_batch_wait",
-    "hsb_alloc_pinned", "hsb_free_pinned", "hsb_measure_h2d_gbs", "hsb_get_dirty_rects", "hsb_get_mirror_dirty_rect", "hsb_download_level_rect", "hsb_download_occupancy_rect",
+    "hsb_alloc_pinned", "hsb_free_pinned", "hsb_measure_h2d_gbs", "hsb_get_dirty_rects", "hsb_pack_dirty_device", "hsb_unpack_dirty_device", "hsb_get_replication_overflows", "hsb_get_mirror_dirty_rect", "hsb_download_level_rect", "hsb_download_occupancy_rect",
     "hsb_get_d2h_bytes", "hsb_covariance_batch", "hsb_get_map_origin", "hsb_get_dist_batch", "hsb_set_cloud_format", "hsb_cloud_to_points", "hsb_match_batch_cloud", "hsb_match_batch_cloud_device",
 ]
 
@@ -136,6 +136,9 @@ def load_library() -> C.CDLL:
     sig("hsb_get_dist_batch", i, vp, i, i, vp, vp, vp, vp, vp)
     sig("hsb_get_dirty_rect", i, vp, i, vp, i)
     sig("hsb_get_dirty_rects", i, vp, vp, i)
+    sig("hsb_pack_dirty_device", i, vp, vp, C.c_size_t, i, vp)
+    sig("hsb_unpack_dirty_device", i, vp, vp, C.c_size_t, vp)
+    sig("hsb_get_replication_overflows", i, vp, ip, i)
     sig("hsb_get_mirror_dirty_rect", i, vp, i, vp, i)
     sig("hsb_download_level_rect", i, vp, i, vp, vp)
     sig("hsb_download_occupancy_rect", i, vp, i, vp, vp)
@@ -653,6 +656,17 @@ class MapRepB200:
     @property
     def d2h_bytes(self) -> int:
         return int(self.lib.hsb_get_d2h_bytes(self.h))
+
+    def pack_dirty_device(self, d_buf: int, capacity_bytes: int, reset: bool = True, stream: int = 0):
+        self._check(self.lib.hsb_pack_dirty_device(self.h, d_buf, int(capacity_bytes), int(reset), stream))
+
+    def unpack_dirty_device(self, d_buf: int, capacity_bytes: int, stream: int = 0):
+        self._check(self.lib.hsb_unpack_dirty_device(self.h, d_buf, int(capacity_bytes), stream))
+
+    def replication_overflows(self, reset: bool = False) -> int:
+        n = C.c_int(0)
+        self._check(self.lib.hsb_get_replication_overflows(self.h, C.byref(n), int(reset)))
+        return int(n.value)
 
     def pack_rect_device(self, level: int, rect, d_buf: int, stream: int = 0):
         r = (C.c_int * 4)(*rect)

@@ -541,7 +541,8 @@ int hsb_create(const hsb_config* cfg, hsb_handle** out) {
     for (int i = 0; i < 8; ++i) HSB_CUDA_C(cudaEventCreateWithFlags(&h->bset[k].chunk_ready[i], cudaEventDisableTiming));
   }
   for (int i = 0; i < 2; ++i) HSB_CUDA_C(cudaEventCreate(&h->ev_time[i]));
-  HSB_CUDA_C(cudaMalloc(&h->d_dirty_all, HSB_MAX_LEVELS * 8 * sizeof(int)));
+  HSB_CUDA_C(cudaMalloc(&h->d_dirty_all, (HSB_MAX_LEVELS * 8 + 4) * sizeof(int)));   // + the replication error counter
+  HSB_CUDA_C(cudaMemset(h->d_dirty_all, 0, (HSB_MAX_LEVELS * 8 + 4) * sizeof(int)));
   HSB_CUDA_C(cudaHostAlloc(&h->h_pin, 64 * sizeof(float), cudaHostAllocMapped));
   HSB_CUDA_C(cudaHostGetDevicePointer(&h->h_pin_dev, h->h_pin, 0));
 
@@ -1797,6 +1798,61 @@ int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const fl
   h->launches++;
   HSB_CUDA(h, cudaGetLastError());
   return order_after(h, (cudaStream_t)stream, true);
+}
+
+static void fill_tile_params(hsb_handle* h, HsbTileParams& T, float* d_buf, size_t capacity_bytes) {
+  memset(&T, 0, sizeof(T));
+  T.levels = h->levels;
+  for (int l = 0; l < h->levels; ++l) {
+    Level& L = h->lv[l];
+    T.lv[l].logodds = L.logodds;
+    T.lv[l].prob = L.prob;
+    T.lv[l].surf = L.surf;
+    T.lv[l].sx = L.sx;
+    T.lv[l].sy = L.sy;
+    T.lv[l].dirty = L.dirty;
+  }
+  T.buf = d_buf;
+  T.capacity_words = (unsigned)std::min<size_t>(capacity_bytes / 4, 0xffffffffu);
+  T.error_count = h->d_dirty_all + HSB_MAX_LEVELS * 8;
+}
+
+int hsb_pack_dirty_device(hsb_handle* h, float* d_buf, size_t capacity_bytes, int reset, void* stream) {
+  if (!h || !d_buf || capacity_bytes < HSB_TILE_HEADER_WORDS * 4) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  HsbTileParams T;
+  fill_tile_params(h, T, d_buf, capacity_bytes);
+  T.reset = reset;
+  int s;
+  if ((s = order_before(h, (cudaStream_t)stream, false)) != HSB_OK) return s;
+  hsb::pack_dirty_kernel<<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(T);
+  if (reset) hsb::reset_dirty_kernel<<<1, 4 * HSB_MAX_LEVELS, 0, (cudaStream_t)stream>>>(T);
+  h->launches += reset ? 2 : 1;
+  HSB_CUDA(h, cudaGetLastError());
+  return order_after(h, (cudaStream_t)stream, false);
+}
+
+int hsb_unpack_dirty_device(hsb_handle* h, const float* d_buf, size_t capacity_bytes, void* stream) {
+  if (!h || !d_buf || capacity_bytes < HSB_TILE_HEADER_WORDS * 4) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  HsbTileParams T;
+  fill_tile_params(h, T, const_cast<float*>(d_buf), capacity_bytes);
+  int s;
+  if ((s = order_before(h, (cudaStream_t)stream, true)) != HSB_OK) return s;
+  hsb::unpack_dirty_kernel<<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(T);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  return order_after(h, (cudaStream_t)stream, true);
+}
+
+int hsb_get_replication_overflows(hsb_handle* h, int* count, int reset) {
+  if (!h || !count) return HSB_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  int* d = h->d_dirty_all + HSB_MAX_LEVELS * 8;
+  HSB_CUDA(h, cudaDeviceSynchronize());
+  HSB_CUDA(h, cudaMemcpy(count, d, sizeof(int), cudaMemcpyDeviceToHost));
+  if (reset) HSB_CUDA(h, cudaMemset(d, 0, sizeof(int)));
+  return HSB_OK;
 }
 
 int hsb_raycast_batch(hsb_handle* h, int level, int B, const int* begin_cells, const int* end_cells, float* out_dist,

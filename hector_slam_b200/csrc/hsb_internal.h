@@ -84,6 +84,28 @@ struct HsbUpdateLevelDev {
   int slot;
 };
 
+// One-shot, host-free tile transport (hsb_pack_dirty_device / hsb_unpack_dirty_device): buffer layout in 4-byte words —
+// [0] magic, [1] levels, [2] overflow (1 = the dirty area did not fit, nothing packed), [3] total cells,
+// [4 + 4 l ..] rectangle {x0, y0, x1, y1} of level l (x1 < x0: clean), [HSB_TILE_HEADER_WORDS ..] the log-odds rows of
+// level 0's rectangle, then level 1's, ...
+#define HSB_TILE_HEADER_WORDS 64
+#define HSB_TILE_MAGIC 0x48534254
+struct HsbTileLevelDev {
+  float* logodds;
+  float* prob;
+  cudaSurfaceObject_t surf;
+  int sx, sy;
+  int* dirty;   // [0..3] replication rectangle, [4..7] host-mirror rectangle
+};
+struct HsbTileParams {
+  HsbTileLevelDev lv[HSB_MAX_LEVELS];
+  int levels;
+  float* buf;
+  unsigned capacity_words;   // whole buffer, header included
+  int reset;                 // pack: clear the replication rectangles afterwards (unless overflowed)
+  int* error_count;          // unpack: incremented when an overflowed buffer arrives
+};
+
 struct HsbUpdateParams {
   HsbUpdateLevelDev lv[HSB_MAX_LEVELS];
   int levels;

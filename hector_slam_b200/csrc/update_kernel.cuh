@@ -469,5 +469,95 @@ __global__ void unpack_rect_kernel(float* __restrict__ logodds, float* __restric
   }
 }
 
+
+// ---- one-shot tile transport: everything the host-synchronous protocol asked the host for stays on the device ----
+// The owner's pack kernel reads the dirty rectangles of all levels from device memory, writes them into the buffer's
+// header and the rectangles' log-odds rows behind it; the replicas' unpack kernel reads the header from the buffer the
+// collective delivered.  No size ever travels through a host, so the whole replication step is stream-ordered: pack ->
+// ONE fixed-size ncclBroadcast -> unpack.
+struct TileLayout {
+  int x0[HSB_MAX_LEVELS], y0[HSB_MAX_LEVELS], w[HSB_MAX_LEVELS], h[HSB_MAX_LEVELS];
+  unsigned off[HSB_MAX_LEVELS + 1];   // cells before level l
+};
+__device__ __forceinline__ void tile_layout_from(const int* rects, int levels, TileLayout& t) {
+  unsigned acc = 0;
+  for (int l = 0; l < levels; ++l) {
+    const int x0 = rects[4 * l], y0 = rects[4 * l + 1], x1 = rects[4 * l + 2], y1 = rects[4 * l + 3];
+    const bool dirty = x1 >= x0 && y1 >= y0;
+    t.x0[l] = x0; t.y0[l] = y0;
+    t.w[l] = dirty ? x1 - x0 + 1 : 0;
+    t.h[l] = dirty ? y1 - y0 + 1 : 0;
+    t.off[l] = acc;
+    acc += (unsigned)t.w[l] * (unsigned)t.h[l];
+  }
+  t.off[levels] = acc;
+}
+
+__global__ void __launch_bounds__(256) pack_dirty_kernel(const __grid_constant__ HsbTileParams P) {
+  __shared__ int rects[4 * HSB_MAX_LEVELS];
+  if (threadIdx.x < 4 * P.levels) rects[threadIdx.x] = P.lv[threadIdx.x >> 2].dirty[threadIdx.x & 3];
+  __syncthreads();
+  TileLayout t;
+  tile_layout_from(rects, P.levels, t);
+  const unsigned total = t.off[P.levels];
+  const bool overflow = (unsigned long long)total + HSB_TILE_HEADER_WORDS > P.capacity_words;
+  int* hdr = reinterpret_cast<int*>(P.buf);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr[0] = HSB_TILE_MAGIC; hdr[1] = P.levels; hdr[2] = overflow ? 1 : 0; hdr[3] = (int)total;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 4 * P.levels) hdr[4 + threadIdx.x] = rects[threadIdx.x];
+  if (overflow) return;
+  float* out = P.buf + HSB_TILE_HEADER_WORDS;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int l = 0;
+    while (i >= t.off[l + 1]) ++l;
+    const unsigned k = i - t.off[l];
+    const unsigned r = k / (unsigned)t.w[l], c = k - r * (unsigned)t.w[l];
+    out[i] = P.lv[l].logodds[(size_t)(t.y0[l] + (int)r) * P.lv[l].sx + (t.x0[l] + (int)c)];
+  }
+}
+// after pack (stream order): the shipped rectangles are forgotten — unless the buffer overflowed and nothing was shipped
+__global__ void reset_dirty_kernel(const __grid_constant__ HsbTileParams P) {
+  const int* hdr = reinterpret_cast<const int*>(P.buf);
+  if (hdr[2] != 0) return;
+  const int l = threadIdx.x >> 2, k = threadIdx.x & 3;
+  if (l < P.levels) P.lv[l].dirty[k] = (k < 2) ? INT_MAX : -1;
+}
+__global__ void __launch_bounds__(256) unpack_dirty_kernel(const __grid_constant__ HsbTileParams P) {
+  const int* hdr = reinterpret_cast<const int*>(P.buf);
+  if (hdr[0] != HSB_TILE_MAGIC || hdr[1] != P.levels || hdr[2] != 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.error_count) atomicAdd(P.error_count, 1);
+    return;
+  }
+  TileLayout t;
+  tile_layout_from(hdr + 4, P.levels, t);
+  const unsigned total = t.off[P.levels];
+  if ((unsigned long long)total + HSB_TILE_HEADER_WORDS > P.capacity_words) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.error_count) atomicAdd(P.error_count, 1);
+    return;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < P.levels && t.w[threadIdx.x] > 0) {   // the replica's host mirror has to follow
+    const int l = threadIdx.x;
+    int* md = P.lv[l].dirty + 4;
+    atomicMin(md + 0, t.x0[l]); atomicMin(md + 1, t.y0[l]);
+    atomicMax(md + 2, t.x0[l] + t.w[l] - 1); atomicMax(md + 3, t.y0[l] + t.h[l] - 1);
+  }
+  const float* in = P.buf + HSB_TILE_HEADER_WORDS;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int l = 0;
+    while (i >= t.off[l + 1]) ++l;
+    const unsigned k = i - t.off[l];
+    const unsigned r = k / (unsigned)t.w[l], c = k - r * (unsigned)t.w[l];
+    const int x = t.x0[l] + (int)c, y = t.y0[l] + (int)r;
+    if (x < 0 || y < 0 || x >= P.lv[l].sx || y >= P.lv[l].sy) continue;   // a foreign geometry must not write out of bounds
+    const size_t off = (size_t)y * P.lv[l].sx + x;
+    const float v = in[i];
+    P.lv[l].logodds[off] = v;
+    const float p = prob_from_logodds(v);
+    P.lv[l].prob[off] = p;
+    if (P.lv[l].surf) surf2Dwrite(p, P.lv[l].surf, x * (int)sizeof(float), y);
+  }
+}
+
 }  // namespace hsb
 #endif

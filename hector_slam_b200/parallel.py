@@ -191,3 +191,27 @@ def broadcast_dirty_tiles(rep, device, src: int = 0, group=None, stats: dict | N
         # `buf` may be recycled by torch's allocator as soon as this function returns: the unpack kernels were
         # queued on torch's current stream, which is the stream the allocator tracks the block on — safe.
     return total
+
+
+def tile_buffer(device, capacity_bytes: int = 4 << 20) -> torch.Tensor:
+    """A device buffer for broadcast_dirty_tiles_async (allocate once, reuse every step)."""
+    return torch.empty(capacity_bytes // 4, dtype=torch.float32, device=device)
+
+
+def broadcast_dirty_tiles_async(rep, buf: torch.Tensor, src: int = 0, group=None) -> None:
+    """The same replication step with no host in the loop: the owner packs the dirty rectangles of all levels AND their
+    descriptions into `buf` on the device (hsb_pack_dirty_device), ONE fixed-size broadcast moves it, the replicas
+    unpack from the buffer's own header (hsb_unpack_dirty_device).  Nothing is read back, nothing synchronises: the
+    three operations are queued on torch's current stream and ordered against the handle's streams inside the C-ABI, so
+    the call costs the host three launches (the two-step protocol needs the rectangle sizes on every host first:
+    ~150 us per step).  If the dirty area exceeds the buffer the owner ships nothing and keeps its rectangles; replicas
+    count that (rep.replication_overflows()) — call broadcast_dirty_tiles() then."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    nbytes = buf.numel() * 4
+    stream = torch.cuda.current_stream(buf.device).cuda_stream
+    if dist.get_rank(group) == src:
+        rep.pack_dirty_device(buf.data_ptr(), nbytes, True, stream)
+    dist.broadcast(buf, src=src, group=group)
+    if dist.get_rank(group) != src:
+        rep.unpack_dirty_device(buf.data_ptr(), nbytes, stream)

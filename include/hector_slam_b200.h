@@ -293,6 +293,20 @@ int hsb_get_dirty_rects(hsb_handle* h, int* rects, int reset);
 int hsb_pack_rect_device(hsb_handle* h, int level, const int rect[4], float* d_buf, void* stream);
 int hsb_unpack_rect_device(hsb_handle* h, int level, const int rect[4], const float* d_buf, void* stream);
 
+/* One-shot tile transport without the host in the loop.  hsb_pack_dirty_device reads the dirty rectangles of ALL levels
+ * on the device and writes a self-describing buffer: a 256-byte header (magic, levels, overflow flag, cell count, the
+ * rectangles) followed by the rectangles' log-odds rows; with `reset` the replication rectangles are cleared afterwards.
+ * hsb_unpack_dirty_device applies such a buffer on a replica (rows, probabilities, texture twin, mirror rectangles),
+ * reading everything it needs from the buffer itself.  Between them ONE collective of a fixed size (`capacity_bytes`,
+ * e.g. 4 MB — a scan dirties 0.3-1 MB) moves the buffer: no size passes through a host, the whole replication step is
+ * stream-ordered.  If the dirty area does not fit, pack sets the overflow flag, ships nothing and keeps the rectangles;
+ * replicas count such buffers (hsb_get_replication_overflows; synchronises) and the caller falls back to the two-step
+ * protocol above (hsb_get_dirty_rects + hsb_pack_rect_device) or a full plane broadcast.  Stream ordering as for
+ * hsb_pack_rect_device / hsb_unpack_rect_device. */
+int hsb_pack_dirty_device(hsb_handle* h, float* d_buf, size_t capacity_bytes, int reset, void* stream);
+int hsb_unpack_dirty_device(hsb_handle* h, const float* d_buf, size_t capacity_bytes, void* stream);
+int hsb_get_replication_overflows(hsb_handle* h, int* count, int reset);
+
 /* ---- after the path: what the node does with the results -------------------------------------*/
 /* nav_msgs/OccupancyGrid cell values of one level, as HectorMappingRos::publishMap derives them
  * (hector_mapping/src/HectorMappingRos.cpp:448-468): 0 where the cell is free (log-odds < 0,

@@ -55,6 +55,55 @@ def test_dirty_rect_pack_unpack(hsb_lib):
     b.close()
 
 
+def test_one_shot_tile_transport(hsb_lib):
+    """hsb_pack_dirty_device / hsb_unpack_dirty_device: the self-describing buffer reproduces the owner's planes on a
+    second handle without any size passing through the host; an undersized buffer ships nothing, keeps the rectangles
+    and is counted on the receiving side."""
+    import torch
+
+    from hector_slam_b200 import capi
+
+    g = load_golden("slam3.npz")
+    a = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+    b = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+    cap = 4 << 20
+    buf = torch.zeros(cap // 4, dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    pose = g["first_hint"]
+    for k in range(4):
+        pose, _ = a.matchData(pose, g["scans"][k])
+        a.updateByScan(g["scans"][k], pose)
+        if k == 1:
+            continue                                          # two writes accumulate in one rectangle
+        rects = a.get_dirty_rects()
+        a.pack_dirty_device(buf.data_ptr(), cap, True, st)
+        b.unpack_dirty_device(buf.data_ptr(), cap, st)       # no synchronisation in between
+        hdr = buf[:64].view(torch.int32).cpu().numpy()
+        assert hdr[1] == 3 and hdr[2] == 0 and hdr[3] == sum((r[2] - r[0] + 1) * (r[3] - r[1] + 1) for r in rects)
+        assert a.get_dirty_rects() == [None, None, None]
+        for l in range(3):
+            assert np.array_equal(a.download_level(l), b.download_level(l))
+            assert np.array_equal(a.download_prob(l), b.download_prob(l))
+            assert b.get_mirror_dirty_rect(l) is not None
+    assert b.replication_overflows() == 0
+    pa, _ = a.matchData(pose, g["scans"][4])
+    pb, _ = b.matchData(pose, g["scans"][4])
+    assert np.array_equal(pa, pb)
+    # undersized buffer: nothing shipped, rectangles kept, replica counts the event
+    a.updateByScan(g["scans"][4], pa)
+    small = 64 * 4 + 1000 * 4
+    before = a.get_dirty_rects()
+    a.pack_dirty_device(buf.data_ptr(), small, True, st)
+    b.unpack_dirty_device(buf.data_ptr(), small, st)
+    assert a.get_dirty_rects() == before and b.replication_overflows(reset=True) == 1 and b.replication_overflows() == 0
+    a.pack_dirty_device(buf.data_ptr(), cap, True, st)       # the full-size buffer then carries it
+    b.unpack_dirty_device(buf.data_ptr(), cap, st)
+    for l in range(3):
+        assert np.array_equal(a.download_level(l), b.download_level(l))
+    a.close()
+    b.close()
+
+
 def _worker(rank, world, port, q):
     import sys
 
@@ -76,12 +125,17 @@ def _worker(rank, world, port, q):
         pose = g["first_hint"]
         shipped = 0
         probes = []
+        tbuf = parallel.tile_buffer(dev)
         for k in range(g["scans"].shape[0]):
             if rank == 0:                                  # the owner runs SLAM and writes the map
                 pose, _ = rep.matchData(pose, g["scans"][k])
                 rep.updateByScan(g["scans"][k], pose)
                 rep.onMapUpdated()
-            shipped += parallel.broadcast_dirty_tiles(rep, dev, src=0)
+            if k % 2:                                      # alternate the two protocols: two-step (sizes via the hosts) ...
+                shipped += parallel.broadcast_dirty_tiles(rep, dev, src=0)
+            else:                                          # ... and one-shot (self-describing buffer, no host in the loop)
+                parallel.broadcast_dirty_tiles_async(rep, tbuf, src=0)
+                shipped += 1
             # straight after the broadcast, no synchronize: the replica's match must already see the new tiles
             pr, _ = rep.match_batch(g["est"][k:k + 1], g["scans"][k], None)
             probes.append(pr[0])
@@ -103,7 +157,7 @@ def _worker(rank, world, port, q):
         gathered = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)
         same_match = all(bool(torch.equal(gathered[0], x)) for x in gathered)
-        q.put((rank, same_map, same_match and same_probe, shipped, float(sums.sum().item())))
+        q.put((rank, same_map, same_match and same_probe and rep.replication_overflows() == 0, shipped, float(sums.sum().item())))
         rep.close()
     finally:
         dist.destroy_process_group()
