@@ -24,7 +24,7 @@ EXPORTED = [
     "hsb_map_coords_pose", "hsb_world_coords_pose", "hsb_match_data", "hsb_match_batch", "hsb_match_batch_device",
     "hsb_hessian_derivs", "hsb_update_by_scan", "hsb_update_level_by_scan", "hsb_on_map_updated",
     "hsb_set_map_update_min_dist_diff", "hsb_set_map_update_min_angle_diff", "hsb_slam_update",
-    "hsb_slam_update_nowait", "hsb_get_last_map_update_pose", "hsb_set_last_map_update_pose",
+    "hsb_slam_update_nowait", "hsb_slam_update_cloud", "hsb_get_last_map_update_pose", "hsb_set_last_map_update_pose",
     "hsb_upload_level", "hsb_download_level", "hsb_download_prob", "hsb_level_logodds_device_ptr",
     "hsb_refresh_level", "hsb_last_error", "hsb_status_string", "hsb_get_launch_count", "hsb_get_gather_mode",
     "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
@@ -112,6 +112,7 @@ def load_library() -> C.CDLL:
     sig("hsb_set_map_update_min_angle_diff", i, vp, f)
     sig("hsb_slam_update", i, vp, vp, vp, i, vp, i, vp, vp, vp)
     sig("hsb_slam_update_nowait", i, vp, vp, vp, i, vp, i, vp, vp, vp)
+    sig("hsb_slam_update_cloud", i, vp, vp, vp, i, vp, i, i, vp, vp, vp, vp)
     sig("hsb_get_last_map_update_pose", i, vp, vp)
     sig("hsb_set_last_map_update_pose", i, vp, vp)
     sig("hsb_upload_level", i, vp, i, vp)
@@ -368,6 +369,21 @@ class MapRepB200:
                        pts.shape[0], _ptr(og), int(bool(map_without_matching)),
                        pose.ctypes.data, cov.ctypes.data, C.addressof(upd)))
         return pose, cov.reshape(3, 3), bool(upd.value)
+
+    def slam_update_cloud(self, pose_hint_world, points_xyz, transform=None, map_without_matching: bool = False,
+                          nowait: bool = False, cov_inout=None):
+        """scanCallback's default branch in one call: cloud -> endpoints (fused), match, gate, map write.
+        -> (pose (3,), cov (3,3), map_updated: bool, kept endpoints: int)"""
+        hint = _f32(pose_hint_world, 3)
+        pts = _f32(points_xyz).reshape(-1, 3)
+        T = None if transform is None else np.ascontiguousarray(transform, dtype=np.float64).reshape(12)
+        pose = np.zeros(3, np.float32)
+        cov = np.zeros(9, np.float32) if cov_inout is None else _f32(cov_inout).reshape(9).copy()
+        upd, kept = C.c_int(0), C.c_int(0)
+        self._check(self.lib.hsb_slam_update_cloud(self.h, hint.ctypes.data, pts.ctypes.data if pts.size else None,
+                                                   pts.shape[0], _ptr(T), int(bool(map_without_matching)), int(bool(nowait)),
+                                                   pose.ctypes.data, cov.ctypes.data, C.addressof(upd), C.addressof(kept)))
+        return pose, cov.reshape(3, 3), bool(upd.value), int(kept.value)
 
     def last_map_update_pose(self) -> np.ndarray:
         out = np.zeros(3, np.float32)

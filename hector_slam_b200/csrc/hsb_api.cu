@@ -75,7 +75,7 @@ struct hsb_handle {
   bool fmt_set = false;
   hsb_cloud_format cfmt = hsb_cloud_format();
   bool cfmt_set = false;
-  DevBuf d_cloud, d_cloud_off, d_cloud_tf, d_origo;
+  DevBuf d_cloud, d_cloud_off, d_cloud_tf, d_origo, d_cloud1;
   int last_n = 0;
   float last_origo[2] = {0.f, 0.f};
   // pinned host scratch
@@ -629,7 +629,7 @@ int hsb_destroy(hsb_handle* h) {
   for (int l = 0; l < HSB_MAX_LEVELS; ++l) destroy_level(h, h->lv[l]);
   DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_gate, &h->d_last_pts, &h->d_upd_pts,
                     &h->d_beam_cs, &h->d_ranges, &h->d_occ, &h->d_trace,
-                    &h->d_cloud, &h->d_cloud_off, &h->d_cloud_tf, &h->d_origo};
+                    &h->d_cloud, &h->d_cloud_off, &h->d_cloud_tf, &h->d_origo, &h->d_cloud1};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (int k = 0; k < 2; ++k) {
@@ -1352,7 +1352,7 @@ static void fill_update_level(hsb_handle* h, int l, HsbUpdateLevelDev& d) {
 // MapRepMultiMap::updateByScan (MapRepMultiMap.h:134-147) as launches on h->stream; level 0 reads `d_pts0`,
 // the coarse levels the container the last matchData left behind (:143).  pose_dev / gate_flag: see HsbUpdateParams.
 static int enqueue_update_by_scan(hsb_handle* h, const float2* d_pts0, int n, const float origo[2], const float pose[3],
-                                  const float* pose_dev, const float* gate_flag) {
+                                  const float* pose_dev, const float* gate_flag, const int* n_dev = nullptr) {
   HsbUpdateParams P;
   memset(&P, 0, sizeof(P));
   P.levels = h->levels;
@@ -1369,11 +1369,13 @@ static int enqueue_update_by_scan(hsb_handle* h, const float2* d_pts0, int n, co
     if (l == 0) {  // MapRepMultiMap.h:140-141
       d.pts = d_pts0;
       d.n = n;
+      d.n_dev = n_dev;   // fused point-cloud step: `n` is the cloud's size, the kept endpoints are counted on the device
       d.origo_x = origo ? origo[0] : 0.f;
       d.origo_y = origo ? origo[1] : 0.f;
     } else {  // :143 — the container left behind by the last matchData
       d.pts = reinterpret_cast<const float2*>(scan_points(h->d_last_pts));
       d.n = h->last_n;
+      d.n_dev = (n_dev && d.pts == d_pts0) ? n_dev : nullptr;   // ... which is this very scan when the step matched it
       d.origo_x = h->last_origo[0];
       d.origo_y = h->last_origo[1];
     }
@@ -1483,6 +1485,120 @@ int hsb_slam_update(hsb_handle* h, const float hint[3], const float* pts, int n,
 int hsb_slam_update_nowait(hsb_handle* h, const float hint[3], const float* pts, int n, const float origo[2],
                            int map_without_matching, float out_pose[3], float cov_inout[9], int* map_updated) {
   return slam_update_impl(h, hint, pts, n, origo, map_without_matching, out_pose, cov_inout, map_updated, false);
+}
+
+// HectorMappingRos::scanCallback's default branch in one call: rosPointCloudToDataContainer (HectorMappingRos.cpp:283,
+// 509-542) + HectorSlamProcessor::update (:297 / HectorSlamProcessor.h:71-113).  The cloud is converted by the match
+// kernel's staging step; the converted endpoints, which the map writer needs too, are written out by the same kernel and
+// their number stays on the device (the writer reads it there), so no host round trip appears between conversion, match,
+// gate and map write.
+int hsb_slam_update_cloud(hsb_handle* h, const float hint[3], const float* points_xyz, int n, const double* transform,
+                          int map_without_matching, int nowait, float out_pose[3], float cov_inout[9], int* map_updated,
+                          int* out_kept) {
+  if (!h || !hint || !out_pose || n < 0 || (n > 0 && !points_xyz)) return HSB_ERR_INVALID_ARG;
+  if (!h->cfmt_set) return fail(h, HSB_ERR_INVALID_ARG, "hsb_set_cloud_format has not been called");
+  DeviceGuard guard(h->device);
+  int s;
+  if ((s = ensure(h, h->d_scratch, 64 * sizeof(float))) != HSB_OK) return s;
+  if (!h->d_gate.p && (s = reset_gate(h)) != HSB_OK) return s;
+  const double* T = transform ? transform : h->cfmt.laser_transform;
+  // staging layout (floats): [0..15] header: hint, thresholds, force, [8] = 0, [9] = n (cloud offsets, as ints);
+  // [16..39] the laser transform (12 doubles); [40..] the cloud
+  const size_t kHdr = 16, kTf = 24;
+  const size_t bytes = (kHdr + kTf + (size_t)n * 3) * sizeof(float);
+  if ((s = ensure(h, h->d_cloud1, bytes + 16)) != HSB_OK) return s;
+  if (bytes > h->h_stage_bytes) {
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr;
+    h->h_stage_bytes = 0;
+    size_t cap = bytes < (64u << 10) ? (64u << 10) : bytes * 2;
+    HSB_CUDA(h, cudaMallocHost(&h->h_stage, cap));
+    h->h_stage_bytes = cap;
+  }
+  float* hs = h->h_stage;
+  memset(hs, 0, kHdr * sizeof(float));
+  hs[0] = hint[0]; hs[1] = hint[1]; hs[2] = hint[2];
+  hs[3] = h->min_dist; hs[4] = h->min_angle; hs[5] = map_without_matching ? 1.f : 0.f;
+  reinterpret_cast<int*>(hs)[8] = 0;
+  reinterpret_cast<int*>(hs)[9] = n;
+  memcpy(hs + kHdr, T, 12 * sizeof(double));
+  if (n > 0) memcpy(hs + kHdr + kTf, points_xyz, (size_t)n * 12);
+  cudaStream_t st = h->stream;
+  HSB_CUDA(h, cudaMemcpyAsync(h->d_cloud1.p, hs, bytes, cudaMemcpyHostToDevice, st));
+  float* d_c = static_cast<float*>(h->d_cloud1.p);
+  const float* d_hdr = d_c;
+  const int* d_offs = reinterpret_cast<const int*>(d_c) + 8;
+  const double* d_tf = reinterpret_cast<const double*>(d_c + kHdr);
+  const float* d_xyz = d_c + kHdr + kTf;
+  float* d_s = static_cast<float*>(h->d_scratch.p);
+  float* d_gate = static_cast<float*>(h->d_gate.p);
+  int* d_n = reinterpret_cast<int*>(d_s + 40);
+  // the container's origo (HectorMappingRos.cpp:516-517) is known on the host: Vector2f(laserPos) * scaleToMap in fp32
+  volatile float ox = (float)T[3], oy = (float)T[7];
+  volatile float sx = ox * h->lv[0].scale, sy = oy * h->lv[0].scale;
+  const float origo[2] = {sx, sy};
+  const bool host_out = true;   // results always travel through mapped host memory here
+  const bool poll = nowait != 0;
+  volatile unsigned* seq = reinterpret_cast<volatile unsigned*>(h->h_pin + 22);
+  unsigned* seq_dev = reinterpret_cast<unsigned*>(h->h_pin_dev + 22);
+  const unsigned seq_value = ++h->step_seq;
+  int* kept_host = reinterpret_cast<int*>(h->h_pin + 24);
+  int* kept_dev = reinterpret_cast<int*>(h->h_pin_dev + 24);
+  DevBuf& pbuf = map_without_matching ? h->d_upd_pts : h->d_last_pts;
+  if ((s = ensure_scan_buf(h, pbuf, n)) != HSB_OK) return s;
+  float2* d_pts_out = reinterpret_cast<float2*>(scan_points(pbuf));
+  (void)host_out;
+  if (!map_without_matching) {
+    HsbMatchParams P;
+    fill_match_params(h, P);
+    P.B = 1;
+    P.hints = d_hdr;
+    P.out_poses = d_s + 8;
+    P.out_cov = h->h_pin_dev + 12;
+    fill_cloud_params(h, P, d_xyz, d_offs, d_tf, nullptr);
+    P.out_pts = d_pts_out;
+    P.out_n = d_n;
+    P.out_n_host = kept_dev;
+    P.gate_state = d_gate;
+    P.gate_in = d_hdr + 3;
+    P.gate_out_host = h->h_pin_dev + 8;
+    P.seq_host = poll ? seq_dev : nullptr;
+    P.seq_value = seq_value;
+    if ((s = launch_match(h, P, n, st)) != HSB_OK) return s;
+    h->last_n = n;   // upper bound until the kept count arrives (the writer reads the exact one on the device)
+    h->last_origo[0] = origo[0];
+    h->last_origo[1] = origo[1];
+  } else {
+    hsb::cloud_to_points_kernel<<<1, 256, 0, st>>>(d_xyz, n, d_tf, h->cfmt.sqr_laser_min_dist, h->cfmt.sqr_laser_max_dist,
+                                                   h->cfmt.laser_z_min_value, h->cfmt.laser_z_max_value, h->lv[0].scale, d_pts_out, d_n);
+    hsb::slam_gate_kernel<<<1, 32, 0, st>>>(d_gate, d_hdr + 3, d_hdr, d_s + 8, h->h_pin_dev + 8, nullptr, 0);
+    hsb::publish_int_kernel<<<1, 32, 0, st>>>(d_n, kept_dev, poll ? seq_dev : nullptr, seq_value);
+    h->launches += 3;
+    HSB_CUDA(h, cudaGetLastError());
+  }
+  if ((s = enqueue_update_by_scan(h, d_pts_out, n, origo, nullptr, d_s + 8, d_gate + 3, d_n)) != HSB_OK) return s;
+  if (poll) {
+    unsigned spins = 0;
+    while (*seq != seq_value) {
+      if ((++spins & 0xfffu) == 0) {
+        cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return fail(h, HSB_ERR_CUDA, "stream failed: %s", cudaGetErrorString(e));
+        if (e == cudaSuccess && *seq != seq_value) return fail(h, HSB_ERR_CUDA, "fused step finished without publishing its pose");
+      }
+    }
+    __sync_synchronize();
+    h->map_write_pending = true;
+  } else {
+    HSB_CUDA(h, cudaStreamSynchronize(st));
+    h->map_write_pending = false;
+  }
+  const int kept = *kept_host;
+  if (!map_without_matching) h->last_n = kept;
+  memcpy(out_pose, h->h_pin + 8, 3 * sizeof(float));
+  if (map_updated) *map_updated = h->h_pin[11] != 0.f;
+  if (cov_inout && kept > 0 && !map_without_matching) memcpy(cov_inout, h->h_pin + 12, 9 * sizeof(float));
+  if (out_kept) *out_kept = kept;
+  return HSB_OK;
 }
 
 int hsb_set_last_map_update_pose(hsb_handle* h, const float pose[3]) {

@@ -48,6 +48,11 @@ struct HsbMatchParams {
   double cloud_tf0[12];
   float sqr_min_dist, sqr_max_dist, z_min, z_max;
   float* out_origo;         // B x 2 (may be null): dataContainer origo = laser position * scaleToMap
+  // fused single-scan SLAM step from a point cloud (B == 1): the converted endpoints are also written out for the map
+  // writer, their number goes to device memory (out_n) and to mapped host memory (out_n_host)
+  float2* out_pts;
+  int* out_n;
+  int* out_n_host;
   float neg_zero;           // -0.0f, deliberately opaque to the compiler (see mul2_exact in match_kernel.cuh)
   // fused SLAM step (B == 1): the gate of HectorSlamProcessor::update evaluated in the kernel's epilogue
   float* gate_state;        // [0..2] lastMapUpdatePose, [3] flag out; nullptr = no gate
@@ -72,7 +77,8 @@ struct HsbUpdateLevelDev {
   float mtw[6];
   float pt_scale;            // applied to points and origo (2^-level), 1 for per-level calls
   const float2* pts;         // scan used for this level
-  int n;
+  int n;                     // number of endpoints — an upper bound when n_dev is set
+  const int* n_dev;          // if set, the number of endpoints is read from device memory (fused point-cloud step)
   float origo_x, origo_y;    // already in the units of `pts` before pt_scale
   uint32_t stamp_base;       // this scan's stamps: base+1 free, base+2 occupied
   int active;

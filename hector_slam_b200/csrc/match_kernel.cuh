@@ -779,6 +779,13 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
         P.out_origo[2 * (size_t)scan] = __fmul_rn((float)T[3], P.scale_to_map);
         P.out_origo[2 * (size_t)scan + 1] = __fmul_rn((float)T[7], P.scale_to_map);
       }
+      if (P.out_pts) {   // fused single-scan step: the map writer reads the converted endpoints from global memory
+        for (int i = t; i < n; i += GT) P.out_pts[i] = spts[i];
+        if (t == 0) {
+          *P.out_n = n;
+          if (P.out_n_host) *P.out_n_host = n;
+        }
+      }
       ns = n;
       staged = true;
     } else if (cap > 0 && n > 0 && (n < cap || (!PACK && cap - 2 >= GT))) {

@@ -199,6 +199,17 @@ __global__ void slam_gate_kernel(float* __restrict__ state, const float* __restr
   }
 }
 
+// map_without_matching step from a point cloud: the kept-endpoint count goes to mapped host memory, then the sequence number
+__global__ void publish_int_kernel(const int* __restrict__ value_dev, int* value_host, unsigned* seq_host, unsigned seq_value) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    *value_host = *value_dev;
+    if (seq_host) {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned*>(seq_host) = seq_value;
+    }
+  }
+}
+
 // Per-level frame of one updateByScan call: the pose as Translation(x,y)*Rotation(psi) in this level's cells and
 // the common start cell of all beams (OccGridMapBase.h:127-137).
 struct BeamFrame {
@@ -278,7 +289,8 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
   int* slot = L.scratch + 8 * L.slot;
   int bx0 = INT_MAX, by0 = INT_MAX, bx1 = -1, by1 = -1;
 
-  for (int b = team0; b < L.n; b += team_stride) {
+  const int n_beams = L.n_dev ? min(*L.n_dev, L.n) : L.n;
+  for (int b = team0; b < n_beams; b += team_stride) {
     int x1, y1;
     if (!beam_end(L, f, b, x1, y1)) continue;
     bx0 = min(bx0, x1); by0 = min(by0, y1); bx1 = max(bx1, x1); by1 = max(by1, y1);

@@ -253,6 +253,17 @@ int hsb_slam_update(hsb_handle* h, const float pose_hint_world[3], const float* 
 int hsb_slam_update_nowait(hsb_handle* h, const float pose_hint_world[3], const float* points_xy, int n,
                            const float origo[2], int map_without_matching, float out_pose_world[3],
                            float cov_inout[9], int* map_updated);
+/* The DEFAULT branch of HectorMappingRos::scanCallback in one call: rosPointCloudToDataContainer
+ * (hector_mapping/src/HectorMappingRos.cpp:283, 509-542) followed by HectorSlamProcessor::update (:297).  points_xyz =
+ * the n Point32 triples of the projected cloud, `transform` = the tf laser transform of this scan (12 doubles, rows of
+ * [R | t]; NULL = the format's), thresholds from hsb_set_cloud_format.  The conversion runs in the match kernel's staging
+ * step, the converted endpoints are handed to the map writer on the device and their number is counted there: no host
+ * round trip between conversion, match, gate and map write.  nowait != 0: return when the pose has arrived (as
+ * hsb_slam_update_nowait).  *out_kept (may be NULL) = number of endpoints the conversion kept.  Results equal
+ * hsb_cloud_to_points followed by hsb_slam_update with the returned origo. */
+int hsb_slam_update_cloud(hsb_handle* h, const float pose_hint_world[3], const float* points_xyz, int n,
+                          const double* transform, int map_without_matching, int nowait, float out_pose_world[3],
+                          float cov_inout[9], int* map_updated, int* out_kept);
 /* lastMapUpdatePose of the fused step (HectorSlamProcessor.h:151) */
 int hsb_get_last_map_update_pose(hsb_handle* h, float out[3]);
 /* ... and its setter, for a host that wrote the map itself (hsb_update_by_scan) between fused steps: the gate of the

@@ -157,3 +157,56 @@ def test_cloud_path_feeds_the_map_writer(hsb_lib, pyoracle, oracle_kinds):
         assert (d > 1e-5).sum() <= 2, (l, int((d > 1e-5).sum()))
     rep.close()
     orc.close()
+
+
+@pytest.mark.parametrize("nowait", [False, True])
+def test_fused_cloud_slam_step_equals_the_two_call_path(hsb_lib, nowait):
+    """hsb_slam_update_cloud (conversion in the match kernel's staging step, endpoints and their count handed to the map
+    writer on the device) == hsb_cloud_to_points followed by hsb_slam_update with the returned origo: same poses, gate
+    decisions, kept counts and planes — incl. map_without_matching steps, an empty cloud and a per-scan transform."""
+    from hector_slam_b200 import capi, synth
+
+    world = synth.World(1, seed=9)
+    rng = np.random.default_rng(14)
+    poses = world.mapping_poses()[:10]
+    T0 = synth.laser_transform(xyz=(0.2, -0.05, 0.3), rpy=(0.01, -0.02, 0.04))
+    clouds = [synth.ranges_to_cloud(world.cast(p) + rng.normal(0, 0.01, 1081)) for p in poses]
+    clouds[3][::5, 2] = 1.7                    # a fifth of scan 3 leaves the z window
+    clouds[6] = np.zeros((0, 3), np.float32)   # an empty cloud: pose = hint, nothing written
+
+    def run(fused):
+        rep = capi.MapRepB200(0.05, 1024, levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+        rep.set_cloud_format(T0, **synth.CLOUD_FORMAT)
+        rep.setMapUpdateMinDistDiff(0.0)
+        rep.setMapUpdateMinAngleDiff(0.0)
+        out = []
+        for k, p in enumerate(poses):
+            hint = p.astype(np.float32)
+            T = synth.laser_transform(rpy=(0.0, 0.01 * k, 0.02)) if k % 4 == 1 else None
+            without = k in (2, 7)
+            if fused:
+                pose, cov, upd, kept = rep.slam_update_cloud(hint, clouds[k], transform=T, map_without_matching=without,
+                                                             nowait=nowait)
+            else:
+                if T is not None:
+                    rep.set_cloud_format(T, **synth.CLOUD_FORMAT)
+                pts, origo = rep.cloud_to_points(clouds[k])
+                if T is not None:
+                    rep.set_cloud_format(T0, **synth.CLOUD_FORMAT)
+                pose, cov, upd = rep.slam_update(hint, pts, map_without_matching=without, origo=origo)
+                kept = pts.shape[0]
+            out.append((pose, upd, kept, cov))
+        rep.onMapUpdated()
+        planes = [rep.download_level(l) for l in range(3)]
+        rep.close()
+        return out, planes
+
+    (a, pa), (b, pb) = run(True), run(False)
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert np.array_equal(x[0], y[0]) and x[1] == y[1] and x[2] == y[2], (k, x[:3], y[:3])
+        if k not in (2, 6, 7):
+            assert np.array_equal(x[3], y[3]), k
+    assert a[6][2] == 0 and 0 < a[3][2] < a[0][2]
+    for l in range(3):
+        assert np.array_equal(pa[l], pb[l]), l
+        assert (pa[l] != 0).sum() > 1000
