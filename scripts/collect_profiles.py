@@ -30,6 +30,7 @@ cp("parity_report.log", "r02_parity_report.log")
 if ntag:
     cp(f"{ntag}_launches.csv", "r02_launches.csv")
     for rep, md, traffic in ((f"{ntag}_match_full.ncu-rep", "r02_match_kernel_ncu.md", "match_kernel_traffic.json"),
+                             (f"{ntag}_match_b65536.ncu-rep", "r02_match_kernel_ncu_b65536.md", None),
                              (f"{ntag}_match_8192.ncu-rep", "r02_match_kernel_8192_ncu.md", "match_kernel_traffic_8192.json"),
                              (f"{ntag}_slam_step.ncu-rep", "r02_slam_step_ncu.md", None)):
         src = os.path.join(G, rep)
