@@ -12,3 +12,4 @@ echo "== single-scan step, gather batch 4 vs 5"; for u in 4 5; do timeout 300 py
 import json,sys; d=json.load(open('$out/${tag}_slam_u$u.json')); c=d['config3_slam_step']; print('unroll $u:', {k:round(v,1) for k,v in c.items() if isinstance(v,float)}, 'k2_ms', d['roofline_k2']['kernel_ms'])"; done
 echo "== bench N=1"; timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; tail -c 600 $out/${tag}_bench.err; head -c 1500 $out/${tag}_bench.json
 echo "== reference arm"; timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_ref.json 2>> $out/${tag}_bench.err
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
