@@ -93,7 +93,7 @@ struct hsb_handle {
   DevBuf d_gate;           // fused SLAM step: lastMapUpdatePose[3], write-the-map flag
   float min_dist = 0.4f, min_angle = 0.13f;   // HectorSlamProcessor.h:62-63 defaults
   // tuning
-  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_lazy = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1, tune_auto_group = 1, tune_stagger = 0;
+  int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1, tune_auto_group = 1, tune_stagger = 0;
   DevBuf d_trace;
   bool map_write_pending = false;   // a nowait SLAM step's map write may still be running on `stream`
   unsigned step_seq = 0;   // sequence number of the fused SLAM steps (host polling, hsb_slam_update_nowait)
@@ -286,7 +286,6 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st,
   P.stagger_ns = h->tune_stagger;
   P.sm_count = h->sm_count;
   P.prefetch = h->tune_prefetch;
-  P.lazy_wait = h->tune_lazy;
   P.pace_slack = h->tune_pace;
   P.pts_cap = cap;
   size_t smem = header + (size_t)Gr * cap * 8;
@@ -738,7 +737,6 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "host_out")) h->tune_host_out = value;
   else if (!strcmp(key, "partial")) h->tune_partial = value;
   else if (!strcmp(key, "prefetch")) h->tune_prefetch = value;
-  else if (!strcmp(key, "lazy")) h->tune_lazy = value;
   else if (!strcmp(key, "trace")) h->tune_trace = value;
   else if (!strcmp(key, "pace")) h->tune_pace = value;
   else if (!strcmp(key, "time_update")) h->tune_time_update = value;

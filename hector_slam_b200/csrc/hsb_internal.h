@@ -64,7 +64,6 @@ struct HsbMatchParams {
   int sm_count;             // SMs of the device (the one-scan-per-CTA shapes derive a warp's rank on its SM from blockIdx)
   int pace_slack;           // > 0: groups of a CTA keep within this many evaluations of the slowest one (see match_kernel)
   int prefetch;             // != 0: L2 bulk prefetch of the part of a scan that is read from global memory
-  int lazy_wait;            // != 0: the first evaluation reads the endpoints from global memory while the bulk copy is in flight
   // diagnostics (hsb_set_tuning "trace"): per scan 8 x u64 = {start, after coarsest level, ..., end (slot 1+levels), -, smid (slot 7)}
   unsigned long long* trace;
 };

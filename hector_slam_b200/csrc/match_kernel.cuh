@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
     }
     const float2* __restrict__ gpts = P.pts + beg;
     const float2* spts_scan = spts;  // shared-memory copy of the scan's first `ns` points (valid when staged)
-    bool staged = false, copy_pending = false, pending_body = false;
+    bool staged = false;
     int ns = 0;                      // points [0, ns) are read from shared memory, [ns, n) from global memory
     if (P.trace && t == 0) P.trace[8 * (size_t)scan] = global_timer_ns();
     if (P.ranges) {
@@ -810,17 +810,11 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
         if (head + body < ns) sdst[ns - 1] = gpts[ns - 1];
       }
       if (P.prefetch && t == 0 && ns < n) l2_prefetch(gpts + ns, gpts + n);
-      // lazy wait: the first evaluation walks the endpoints in global memory (same values, same order) while the bulk
-      // copy is in flight, so a cold one-wave launch does not sit out the DRAM fetch of all scans before its first gather
-      copy_pending = P.lazy_wait != 0 && !PACK;
-      if (!copy_pending) {
-        if (body > 0) {
-          mbar_wait(mbar, phase);
-          phase ^= 1u;
-        }
-        group_sync<W>(g);  // head/tail stores visible to the whole group
+      if (body > 0) {
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
       }
-      pending_body = body > 0;
+      group_sync<W>(g);  // head/tail stores visible to the whole group
       spts_scan = sdst;
       staged = true;
     } else if (P.prefetch && t == 0 && n > 0) {
@@ -860,17 +854,8 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
           if (PACK && staged)
             eval_pairs<(U + 1) / 2>(LR, reinterpret_cast<const float4*>(spts), t, GT, npairs, cs, ss, ex, ey, P.neg_zero, a);
           else if (staged) {
-            const int nsh = copy_pending ? 0 : ns;
-            eval_points<MODE, U>(LR, spts_scan, t, GT, nsh, cs, ss, ex, ey, a);
-            if (nsh < n) eval_points<MODE, U>(LR, gpts, nsh + t, GT, n, cs, ss, ex, ey, a);
-            if (copy_pending) {
-              if (pending_body) {
-                mbar_wait(mbar, phase);
-                phase ^= 1u;
-              }
-              group_sync<W>(g);
-              copy_pending = false;
-            }
+            eval_points<MODE, U>(LR, spts_scan, t, GT, ns, cs, ss, ex, ey, a);
+            if (ns < n) eval_points<MODE, U>(LR, gpts, ns + t, GT, n, cs, ss, ex, ey, a);
           } else
             eval_points<MODE, U>(LR, gpts, t, GT, n, cs, ss, ex, ey, a);
           warp_reduce(a);
@@ -931,13 +916,6 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
         wpsi = epsi;
         if (P.trace && t == 0) P.trace[8 * (size_t)scan + (P.levels - lvl)] = global_timer_ns();
       }
-    }
-    if (copy_pending) {   // no evaluation consumed the copy (a level list without evaluations): the slots are reused
-      if (pending_body) {
-        mbar_wait(mbar, phase);
-        phase ^= 1u;
-      }
-      group_sync<W>(g);
     }
     if (pace && n <= 0) {   // nothing evaluated: account for the evaluations the others wait for
       for (int lvl = 0; lvl < P.levels; ++lvl) evals_done += P.lv[lvl].evals;

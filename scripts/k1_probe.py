@@ -50,13 +50,11 @@ def timed(iters=20):
     return min(best), float(np.median(best))
 
 
-base = dict(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=0, prefetch=0, trace=0, seq=0, pace=0, auto_group=0, lazy=0)
+base = dict(warps_per_scan=0, scans_per_block=0, stage_smem=1, unroll=0, partial=0, prefetch=0, trace=0, seq=0, pace=0, auto_group=0)
 variants = [
     ("G=1 unstaged (round-1 shape)", {}),
     ("G=1 partial staging", dict(partial=1)),
     ("auto (grouped, staged prefix)", dict(auto_group=1, partial=1)),
-    ("auto + lazy wait", dict(auto_group=1, partial=1, lazy=1)),
-    ("G=1 partial staging + lazy wait", dict(partial=1, lazy=1)),
 ]
 for G in (28, 14):
     for pace in (0, 1):
@@ -64,8 +62,7 @@ for G in (28, 14):
             variants.append((f"G={G} pace={pace} " + ("staged prefix" if stage else "unstaged"),
                              dict(warps_per_scan=1, scans_per_block=G, pace=pace, stage_smem=stage, partial=part)))
 if B > 8192:   # many waves: only the staging question matters
-    variants = [("default", {}), ("default + lazy wait", dict(lazy=1)), ("always fully staged", dict(stage_smem=2)),
-                ("never staged", dict(stage_smem=0))]
+    variants = [("default", {}), ("always fully staged", dict(stage_smem=2)), ("never staged", dict(stage_smem=0))]
 ref = None
 for name, kw in variants:
     t = dict(base)
@@ -149,6 +146,5 @@ if B > 8192:
 timeline("G=1 unstaged (round-1 shape)", {})
 slot_study()
 timeline("auto (grouped, staged prefix)", dict(auto_group=1, partial=1))
-timeline("auto + lazy wait", dict(auto_group=1, partial=1, lazy=1))
 rep.set_tuning(**base)
 rep.close()
