@@ -320,6 +320,16 @@ def time_device_steps(torch, dist, world_size, dev, fn, steps, warmup):
     return float(t.item()), step_ms
 
 
+def pcie_bound(h2d_bytes, gbs, B, world_size, e2e_value):
+    """What the host link alone allows: the step's input bytes at the H2D rate measured in this process (rank 0's link;
+    every rank has its own), and the share of it the pipelined call reaches."""
+    if not gbs:
+        return None
+    floor_ms = h2d_bytes / (gbs * 1e9) * 1e3
+    bound = B * world_size / (floor_ms * 1e-3)
+    return {"h2d_floor_ms_per_step": floor_ms, "value_if_only_the_copy_counted": bound, "frac": e2e_value / bound}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -559,15 +569,20 @@ def main():
                     "host_buffers": "hsb_alloc_pinned (cudaHostAlloc), process bound to the GPU's NUMA node"
                                     if prev_affinity is not None else "hsb_alloc_pinned (NUMA node of the GPU unknown)",
                     "raw_h2d_gbs": h2d_gbs,
+                    "pcie_bound": pcie_bound(int(ranges.nbytes + hints.nbytes), h2d_gbs["ranges"], B, world_size, e2e_value),
                     "max_abs_diff_vs_device_path": same},
             "e2e_endpoints": {"value": e2e_xy_value, "unit": "scan-matches/s",
                               "h2d_bytes_per_step": int(pts.nbytes + hints.nbytes + offs.nbytes),
                               "d2h_bytes_per_step": int(B * 12 + B * 36),
+                              "pcie_bound": pcie_bound(int(pts.nbytes + hints.nbytes + offs.nbytes), h2d_gbs["endpoints"], B,
+                                                       world_size, e2e_xy_value),
                               "call": "hsb_match_batch_submit / _wait: DataContainer endpoints (8 B each) in — the format "
                                       "MapRepresentationInterface::matchData carries"},
             "e2e_cloud": {"value": e2e_cloud_value, "unit": "scan-matches/s",
                           "h2d_bytes_per_step": int(cloud_all.nbytes + hints.nbytes + c_offs.nbytes),
                           "d2h_bytes_per_step": int(B * 12 + B * 36 + B * 8),
+                          "pcie_bound": pcie_bound(int(cloud_all.nbytes + hints.nbytes + c_offs.nbytes), h2d_gbs["endpoints"],
+                                                   B, world_size, e2e_cloud_value),
                           "call": "hsb_match_batch_cloud_submit / _wait: sensor_msgs/PointCloud points (12 B each) in, "
                                   "rosPointCloudToDataContainer fused into the match kernel (the node's default path)"},
             "gpu_launches": int(launches),
