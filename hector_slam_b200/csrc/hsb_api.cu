@@ -1749,6 +1749,36 @@ int hsb_download_occupancy(hsb_handle* h, int level, int8_t* out) {
   return HSB_OK;
 }
 
+// the likelihood launch on device pointers; `st` may be a caller's stream (ordered behind a pending map write)
+static int likelihood_device(hsb_handle* h, int level, int B, const float* d_poses, const float2* d_pts, const int* d_off,
+                             int n_shared, float* d_out, cudaStream_t st) {
+  if (h->map_write_pending && st != h->stream) {
+    HSB_CUDA(h, cudaEventRecord(h->ev_sync[0], h->stream));
+    HSB_CUDA(h, cudaStreamWaitEvent(st, h->ev_sync[0], 0));
+  }
+  HsbLevelDev L;
+  fill_level_dev(h, level, L);
+  int blocks = std::min((B + 3) / 4, h->sm_count * 16);
+  if (h->gather_mode == HSB_GATHER_TEX)
+    hsb::likelihood_kernel<hsb::MODE_TEX><<<blocks, 128, 0, st>>>(L, B, d_poses, d_pts, d_off, d_off ? 0 : n_shared, d_out);
+  else
+    hsb::likelihood_kernel<hsb::MODE_LDG><<<blocks, 128, 0, st>>>(L, B, d_poses, d_pts, d_off, d_off ? 0 : n_shared, d_out);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  return HSB_OK;
+}
+
+int hsb_likelihood_batch_device(hsb_handle* h, int level, int B, const float* d_poses_world, const float* d_points_xy,
+                                const int* d_offsets, int n_shared, float* d_out_likelihood, void* stream) {
+  if (!h || level < 0 || level >= h->levels || B < 0 || !d_poses_world || !d_out_likelihood) return HSB_ERR_INVALID_ARG;
+  if (!d_offsets && n_shared < 0) return HSB_ERR_INVALID_ARG;
+  if (B == 0) return HSB_OK;
+  if (!d_points_xy && (d_offsets || n_shared > 0)) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  DeviceGuard guard(h->device);
+  return likelihood_device(h, level, B, d_poses_world, reinterpret_cast<const float2*>(d_points_xy), d_offsets, n_shared,
+                           d_out_likelihood, (cudaStream_t)stream);
+}
+
 int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses, const float* pts, const int* offsets,
                          int n_shared, float* out) {
   if (!h || level < 0 || level >= h->levels || B < 0 || !poses || !out) return HSB_ERR_INVALID_ARG;
@@ -1765,21 +1795,11 @@ int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses, co
   HSB_CUDA(h, cudaMemcpyAsync(h->d_hints.p, poses, (size_t)B * 12, cudaMemcpyHostToDevice, st));
   if (total > 0) HSB_CUDA(h, cudaMemcpyAsync(h->d_pts.p, pts, total * 8, cudaMemcpyHostToDevice, st));
   if (offsets) HSB_CUDA(h, cudaMemcpyAsync(h->d_offsets.p, offsets, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, st));
-  HsbLevelDev L;
-  fill_level_dev(h, level, L);
-  int blocks = std::min((B + 3) / 4, h->sm_count * 16);
-  const int* d_off = offsets ? static_cast<const int*>(h->d_offsets.p) : nullptr;
   float* d_out = static_cast<float*>(h->d_poses.p);
-  if (h->gather_mode == HSB_GATHER_TEX)
-    hsb::likelihood_kernel<hsb::MODE_TEX><<<blocks, 128, 0, st>>>(L, B, static_cast<const float*>(h->d_hints.p),
-                                                                  static_cast<const float2*>(h->d_pts.p), d_off,
-                                                                  offsets ? 0 : n_shared, d_out);
-  else
-    hsb::likelihood_kernel<hsb::MODE_LDG><<<blocks, 128, 0, st>>>(L, B, static_cast<const float*>(h->d_hints.p),
-                                                                  static_cast<const float2*>(h->d_pts.p), d_off,
-                                                                  offsets ? 0 : n_shared, d_out);
-  h->launches++;
-  HSB_CUDA(h, cudaGetLastError());
+  s = likelihood_device(h, level, B, static_cast<const float*>(h->d_hints.p), static_cast<const float2*>(h->d_pts.p),
+                        offsets ? static_cast<const int*>(h->d_offsets.p) : nullptr, offsets ? 0 : (n_shared > 0 ? n_shared : 0),
+                        d_out, st);
+  if (s != HSB_OK) return s;
   HSB_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   HSB_CUDA(h, cudaStreamSynchronize(st));
   return HSB_OK;

@@ -342,6 +342,11 @@ uint64_t hsb_get_d2h_bytes(const hsb_handle* h);
  * hypotheses; the reference only uses it in its (dead) sigma-point covariance.  Host buffers. */
 int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses_world, const float* points_xy,
                          const int* offsets, int n_shared, float* out_likelihood);
+/* The same on DEVICE pointers, enqueued on `stream` (ordered behind a pending map write of the handle, nothing is
+ * synchronised): scores the output of hsb_match_batch_device where it lies — a relocalisation step is match -> score ->
+ * arg-max without a host round trip.  Same values as the host call. */
+int hsb_likelihood_batch_device(hsb_handle* h, int level, int B, const float* d_poses_world, const float* d_points_xy,
+                                const int* d_offsets, int n_shared, float* d_out_likelihood, void* stream);
 
 /* OccGridMapUtil::getCovarianceForPose — map/OccGridMapUtil.h:106-160 — the sigma-point covariance of a pose: the
  * likelihoods (above) of the pose and of six neighbours (+-1.5 cells in x / y, +-0.05 rad) weight a mean and a 3x3

@@ -58,6 +58,24 @@ def test_likelihood_batch(hsb_lib, pyoracle, oracle_kinds, mode):
     hyp = np.stack([g["hints"][0], g["ref_poses"][0], g["truth"][0].astype(np.float32)])
     sc = rep.likelihood_batch(0, hyp, g["scans"][0], None)
     assert sc[1] > sc[0] and sc[2] > sc[0]
+    # the device-pointer entry point (what a relocalisation step chains behind hsb_match_batch_device): same bits,
+    # per-scan offsets and the shared-scan layout, on a caller's stream
+    import torch
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(device=dev)
+    d_poses, d_pts, d_offs = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (poses, pts, offs))
+    d_out = torch.full((K,), -7.0, dtype=torch.float32, device=dev)
+    for l in range(3):
+        with torch.cuda.stream(side):
+            rep.likelihood_batch_device(l, K, d_poses.data_ptr(), d_pts.data_ptr(), d_offs.data_ptr(), 0, d_out.data_ptr(),
+                                        side.cuda_stream)
+        side.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), rep.likelihood_batch(l, poses, pts, offs))
+    d_hyp, d_scan = torch.from_numpy(hyp).to(dev), torch.from_numpy(np.ascontiguousarray(g["scans"][0])).to(dev)
+    d_sc = torch.empty(3, dtype=torch.float32, device=dev)
+    rep.likelihood_batch_device(0, 3, d_hyp.data_ptr(), d_scan.data_ptr(), None, g["scans"].shape[1], d_sc.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sc.cpu().numpy(), sc)
     rep.close()
     orc.close()
 
