@@ -320,6 +320,24 @@ def time_device_steps(torch, dist, world_size, dev, fn, steps, warmup):
     return float(t.item()), step_ms
 
 
+TLD4_CYCLES_PER_WARP_GATHER = 15.96   # measured: scripts/ubench/tex_rate.cu, profiles/r02_tex_rate.log (scan-like footprints)
+
+
+def tex_pipe_ceiling(matches_per_s_per_gpu, clocks):
+    """The roof that binds K1: an sm_100a SM returns one warp-level TLD4 (4 fp32 x 32 lanes) every ~16 cycles, whatever
+    the footprints' spread; no other path delivers the four neighbours cheaper (profiles/r02_tex_rate.log).  A match
+    issues EVALS x ceil(N_PTS / 32) warp-gathers."""
+    import torch
+
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    wg = EVALS * ((N_PTS + 31) // 32)
+    ceiling = sms * mhz * 1e6 / (wg * TLD4_CYCLES_PER_WARP_GATHER)
+    return {"cycles_per_warp_gather": TLD4_CYCLES_PER_WARP_GATHER, "warp_gathers_per_match": wg, "sm_mhz": mhz,
+            "ceiling": ceiling, "unit": "scan-matches/s per GPU", "frac": matches_per_s_per_gpu / ceiling,
+            "source": "profiles/r02_tex_rate.log (scripts/ubench/tex_rate.cu)"}
+
+
 def pcie_bound(h2d_bytes, gbs, B, world_size, e2e_value):
     """What the host link alone allows: the step's input bytes at the H2D rate measured in this process (rank 0's link;
     every rank has its own), and the share of it the pipelined call reaches."""
@@ -597,6 +615,7 @@ def main():
                                  "(DRAM traffic = the endpoints, once: dram_frac), so HBM is not the roof of this "
                                  "configuration and frac > 1 is expected — the unit that binds is the L1TEX texture "
                                  "write-back path (bound_unit_frac, ncu) together with instruction issue (issue_frac)",
+                         "tex_pipe": tex_pipe_ceiling(value / world_size, clocks),
                          "peak_source": peak_src, "kernel": "hsb::match_kernel",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": BYTES_PER_MATCH * B},
             "clocks": clocks,

@@ -7,6 +7,8 @@
 //   rg x2     2 x tex.2d on an RG32F array          (two 8-byte texels: rows y and y+1 of a pair plane)
 //   r x1      tex.2d on an R32F array, one value    (the pipe's rate for a 1-register return)
 //   ldg128    ld.global.v4 from a linear float4 plane (the LSU path with the same packed neighbourhood)
+//   ldg64x2   2 x ld.global.v2 from a pair plane;  ldg32x4: 4 x ld.global.f32 from the plain plane (K1's MODE_LDG)
+//   tld4+128 / tld4+64: every other gather through the texture path, the others through the LSU path — do they overlap?
 // Output: ns and SM cycles (at the clock measured in the kernel) per warp-level gather per SM, 28 warps per SM.
 // Build: make -C scripts/ubench bin/tex_rate     Run: bin/tex_rate [map size, default 2048]
 #include <cuda_runtime.h>
@@ -17,7 +19,7 @@
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1);} } while (0)
 
-enum Op { OP_TLD4 = 0, OP_RGBA = 1, OP_RG2 = 2, OP_R1 = 3, OP_LDG128 = 4 };
+enum Op { OP_TLD4 = 0, OP_RGBA = 1, OP_RG2 = 2, OP_R1 = 3, OP_LDG128 = 4, OP_LDG64X2 = 5, OP_LDG32X4 = 6, OP_MIX128 = 7, OP_MIX64 = 8 };
 enum Pattern { PAT_SAME = 0, PAT_CONSEC = 1, PAT_WINDOW = 2, PAT_RANDOM = 3, PAT_SCAN = 4 };
 
 struct Args {
@@ -45,11 +47,28 @@ __device__ __forceinline__ float gather(const Args& A, float x, float y) {
   } else if (OP == OP_R1) {
     float t0, t1, t2;
     asm volatile("tex.2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6}];" : "=f"(v.x), "=f"(t0), "=f"(t1), "=f"(t2) : "l"(A.tex), "f"(x), "f"(y));
-  } else {
+  } else if (OP == OP_LDG128) {
     const int ix = (int)x, iy = (int)y;
     v = __ldg(A.plane + (size_t)iy * A.size + ix);
+  } else if (OP == OP_LDG64X2) {   // pair plane: {P(x,y), P(x+1,y)} per cell, rows y and y+1
+    const int ix = (int)x, iy = (int)y;
+    const float2* pl = reinterpret_cast<const float2*>(A.plane);
+    const float2 a = __ldg(pl + (size_t)iy * A.size + ix), b = __ldg(pl + (size_t)(iy + 1) * A.size + ix);
+    v = make_float4(a.x, a.y, b.x, b.y);
+  } else {   // OP_LDG32X4: the plain plane, four scalar loads (K1's MODE_LDG)
+    const int ix = (int)x, iy = (int)y;
+    const float* pl = reinterpret_cast<const float*>(A.plane);
+    const float* r0 = pl + (size_t)iy * A.size + ix;
+    v = make_float4(__ldg(r0), __ldg(r0 + 1), __ldg(r0 + A.size), __ldg(r0 + A.size + 1));
   }
   return (v.x + v.y) + (v.z + v.w);
+}
+// mixes: gathers alternate between the texture path and the load/store path — do the two overlap?
+template <int OP, int u>
+__device__ __forceinline__ float gather_mix(const Args& A, float x, float y) {
+  if (OP == OP_MIX128) return (u & 1) ? gather<OP_LDG128>(A, x, y) : gather<OP_TLD4>(A, x, y);
+  if (OP == OP_MIX64) return (u & 1) ? gather<OP_LDG64X2>(A, x, y) : gather<OP_TLD4>(A, x, y);
+  return gather<OP>(A, x, y);
 }
 
 template <int OP, int U>
@@ -85,7 +104,7 @@ __global__ void __launch_bounds__(896, 1) rate_kernel(const Args A) {
     }
     float r[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) r[u] = gather<OP>(A, xs[u], ys[u]);
+    for (int u = 0; u < U; ++u) r[u] = (u & 1) ? gather_mix<OP, 1>(A, xs[u], ys[u]) : gather_mix<OP, 0>(A, xs[u], ys[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) acc += r[u];
   }
@@ -174,5 +193,9 @@ int main(int argc, char** argv) {
   A.tex = t1;
   run<OP_R1>("r x1", A, sms, warps, pats);
   run<OP_LDG128>("ldg128", A, sms, warps, pats);
+  run<OP_LDG64X2>("ldg64x2", A, sms, warps, pats);
+  run<OP_LDG32X4>("ldg32x4", A, sms, warps, pats);
+  run<OP_MIX128>("tld4+128", A, sms, warps, pats);
+  run<OP_MIX64>("tld4+64", A, sms, warps, pats);
   return 0;
 }
