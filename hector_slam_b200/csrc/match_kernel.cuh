@@ -148,6 +148,11 @@ __device__ __forceinline__ void solve3(const Acc& s, float& o0, float& o1, float
 //    (profiles/r02_k1_variants.log) 32.7 vs 34.3 M matches/s at 65 536 scans per launch, equal at 4096.  The kernel is
 //    bound by the texture pipe, and the branchy form consumes the gathers one by one as they return (DEPBAR per
 //    endpoint) where the predicated form waits for them in pairs.  Off.
+// HSB_DIAG: 1 compiles the diagnostics in (tuning keys trace / pace / stagger / prefetch: scripts/k1_probe.py);
+// 0 removes them from the kernel (scripts/variant_timing.py measures what carrying them costs).
+#ifndef HSB_DIAG
+#define HSB_DIAG 1
+#endif
 #ifndef HSB_PRED_ACC
 #define HSB_PRED_ACC 0
 #endif
@@ -727,7 +732,7 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
   // therefore publish how many evaluations they have completed and a group that is more than `pace_slack` ahead of
   // the slowest one sleeps: its issue slots and texture bandwidth go to the stragglers and all scans of the CTA end
   // within ~pace_slack evaluations of each other.  No arithmetic is involved: results are unchanged.
-  const bool pace = (G > 1) && P.pace_slack > 0;
+  const bool pace = HSB_DIAG && (G > 1) && P.pace_slack > 0;
   int evals_done = 0;
   if (G > 1) {
     if (threadIdx.x < 32) prog[threadIdx.x] = 0x7fffffff;   // slots of absent / finished groups never hold anyone back
@@ -742,7 +747,7 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
   // that bounds this kernel, idles.  Many-wave batches do not show this (finished scans are replaced at arbitrary
   // moments: 95 % texture utilisation against ~83 % in one wave).  Starting the warps of an SM a fraction of an
   // evaluation apart de-phases them for the whole launch.
-  if (P.stagger_ns > 0) {
+  if (HSB_DIAG && P.stagger_ns > 0) {
     const int rank = (G > 1) ? g : (int)((blockIdx.x / (unsigned)max(P.sm_count, 1)) & 31u);
     if (rank > 0) __nanosleep((unsigned)min(rank * P.stagger_ns, 1000000));
   }
@@ -764,7 +769,7 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
     const float2* spts_scan = spts;  // shared-memory copy of the scan's first `ns` points (valid when staged)
     bool staged = false;
     int ns = 0;                      // points [0, ns) are read from shared memory, [ns, n) from global memory
-    if (P.trace && t == 0) P.trace[8 * (size_t)scan] = global_timer_ns();
+    if (HSB_DIAG && P.trace && t == 0) P.trace[8 * (size_t)scan] = global_timer_ns();
     if (P.ranges) {
       // raw ranges in: convert + compact straight into shared memory (host guarantees cap >= n_beams)
       n = stage_from_ranges<W>(P.ranges + (size_t)scan * P.n_beams, P.beam_cs, P.n_beams, P.range_min, P.range_max_c,
@@ -809,7 +814,7 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
         if (head) sdst[0] = gpts[0];
         if (head + body < ns) sdst[ns - 1] = gpts[ns - 1];
       }
-      if (P.prefetch && t == 0 && ns < n) l2_prefetch(gpts + ns, gpts + n);
+      if (HSB_DIAG && P.prefetch && t == 0 && ns < n) l2_prefetch(gpts + ns, gpts + n);
       if (body > 0) {
         mbar_wait(mbar, phase);
         phase ^= 1u;
@@ -817,7 +822,7 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
       group_sync<W>(g);  // head/tail stores visible to the whole group
       spts_scan = sdst;
       staged = true;
-    } else if (P.prefetch && t == 0 && n > 0) {
+    } else if (HSB_DIAG && P.prefetch && t == 0 && n > 0) {
       l2_prefetch(gpts, gpts + n);
     }
 
@@ -914,14 +919,14 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
         epsi = normalize_angle(epsi);                 // ScanMatcher.h:170
         affine_apply_exact(L.wtm, ex, ey, wx, wy);    // :186 getWorldCoordsPose
         wpsi = epsi;
-        if (P.trace && t == 0) P.trace[8 * (size_t)scan + (P.levels - lvl)] = global_timer_ns();
+        if (HSB_DIAG && P.trace && t == 0) P.trace[8 * (size_t)scan + (P.levels - lvl)] = global_timer_ns();
       }
     }
     if (pace && n <= 0) {   // nothing evaluated: account for the evaluations the others wait for
       for (int lvl = 0; lvl < P.levels; ++lvl) evals_done += P.lv[lvl].evals;
       if (t == 0) prog[g] = evals_done;
     }
-    if (P.trace && t == 0) {
+    if (HSB_DIAG && P.trace && t == 0) {
       P.trace[8 * (size_t)scan + 1 + P.levels] = global_timer_ns();
       P.trace[8 * (size_t)scan + 6] = warp_id();
       P.trace[8 * (size_t)scan + 7] = sm_id();

@@ -13,6 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
+    "shipped flags, diagnostics compiled in": ["-DHSB_DIAG=1"],
+    "shipped flags, diagnostics compiled OUT": ["-DHSB_DIAG=0"],
+}
+OLD_VARIANTS = {
     "uniform handle only": ["-DHSB_UNIFORM_HANDLE=1", "-DHSB_TLD4_OFFSET=0", "-DHSB_PRED_ACC=0"],
     "uniform + TLD4.AOFFI": ["-DHSB_UNIFORM_HANDLE=1", "-DHSB_TLD4_OFFSET=1", "-DHSB_PRED_ACC=0"],
     "uniform + predicated acc": ["-DHSB_UNIFORM_HANDLE=1", "-DHSB_TLD4_OFFSET=0", "-DHSB_PRED_ACC=1"],
@@ -42,15 +46,10 @@ def run(name):
         d_o = torch.from_numpy(o).to(dev)
         d_p = torch.empty((B, 3), dtype=torch.float32, device=dev)
         if B == 4096:
-            configs = [("G=1 unstaged", dict(stage_smem=0)), ("G=1 staged prefix", dict(stage_smem=1, partial=1))]
-            for st in (0, 100, 200, 350, 700):
-                configs.append((f"G=28 unstaged stagger={st}", dict(warps_per_scan=1, scans_per_block=28, stage_smem=0, stagger=st)))
-                configs.append((f"G=28 prefix   stagger={st}", dict(warps_per_scan=1, scans_per_block=28, stage_smem=1, partial=1, stagger=st)))
-            for st in (200, 350):
-                configs.append((f"G=1 unstaged stagger={st}", dict(stage_smem=0, stagger=st)))
-                configs.append((f"G=1 prefix   stagger={st}", dict(stage_smem=1, partial=1, stagger=st)))
+            configs = [("auto (grouped, staged prefix)", dict(auto_group=1, partial=1)),
+                       ("G=1 staged prefix", dict(stage_smem=1, partial=1)), ("G=1 unstaged", dict(stage_smem=0))]
         else:
-            configs = [("G=1 staged", dict(stage_smem=2)), ("G=1 unstaged", dict(stage_smem=0))]
+            configs = [("G=1 staged (default)", dict(stage_smem=1, partial=1)), ("G=1 unstaged", dict(stage_smem=0))]
         for cname, kw in configs:
             rep.set_tuning(warps_per_scan=0, scans_per_block=0, stage_smem=1, partial=0, pace=0, auto_group=0, stagger=0)
             rep.set_tuning(**kw)
