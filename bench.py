@@ -815,7 +815,8 @@ def extra_config5(torch, dist, capi, synth, parallel, new_rep, rank, world_size,
             match(i)
             if rank == 0:
                 torch.cuda.current_stream().synchronize()   # the owner's map write must not overtake its own match
-                rep.slam_update(whints[i % 16], wscans[i % 16])
+                # nowait: back as soon as the pose is known; the tile pack below is stream-ordered behind the map write
+                rep.slam_update(whints[i % 16], wscans[i % 16], nowait=True)
             t0 = time.perf_counter()
             if one_shot[0]:
                 parallel.broadcast_dirty_tiles_async(rep, tbuf, src=0)

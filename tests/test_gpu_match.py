@@ -264,6 +264,58 @@ def test_batch_parity_against_oracle_2048_three_levels(hsb_lib, pyoracle, oracle
     orc.close()
 
 
+def test_long_scans_maximum_sizes(hsb_lib, pyoracle, oracle_kinds):
+    """Scans far longer than a lidar's 1081 beams (a projected 3-D cloud): 40 000 endpoints do not fit the 227 KB of
+    shared memory of any launch shape, so the staged-prefix / unstaged paths of the single-scan (8 warps) and of the
+    batch launch are what runs.  Against the oracle, plus a ragged batch mixing long, short and empty scans."""
+    from hector_slam_b200 import capi, synth
+
+    kind = "reference" if "reference" in oracle_kinds else "port"
+    world = synth.World.for_map_size(2048)
+    orc = pyoracle.Oracle(kind, 0.05, 2048, 3)
+    orc.set_update_factors(0.4, 0.9)
+    pyoracle.build_map_known_poses(orc, world)
+    rep = capi.MapRepB200(0.05, 2048, levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+    for l in range(3):
+        rep.upload_level(l, orc.get_logodds(l))
+    rng = np.random.default_rng(77)
+    poses = world.sample_free_poses(5, rng)
+    hints = synth.perturb_hints(poses, seed=5, dxy=0.05, dpsi=0.02)
+    longs = []
+    for k, p in enumerate(poses):   # 37 noisy casts from the same pose, concatenated: 39 997 endpoints
+        longs.append(np.concatenate([synth.make_scan(world, p, np.random.default_rng(1000 * k + r)) for r in range(37)]))
+    assert all(s.shape[0] > 39000 for s in longs)
+    # one long scan through hsb_match_data
+    want, _ = orc.match(hints[0], longs[0])
+    got, cov = rep.matchData(hints[0], longs[0])
+    report(f"long scan (39 997 endpoints) single: pose diff {pose_err(got, want)}")
+    check_poses(got, want, "long single scan")
+    assert np.all(np.isfinite(cov))
+    # ragged batch: long, short, empty, long, a 3-point scan, long ...
+    short = synth.make_scan(world, poses[1], np.random.default_rng(9))
+    items = [longs[0], short, np.zeros((0, 2), np.float32), longs[2], short[:3], longs[3], longs[4]]
+    hh = hints[[0, 1, 1, 2, 1, 3, 4]]
+    pts = np.ascontiguousarray(np.concatenate(items), dtype=np.float32)
+    offs = np.concatenate([[0], np.cumsum([s.shape[0] for s in items])]).astype(np.int32)
+    P, C = rep.match_batch(hh, pts, offs)
+    W, _, _ = orc.match_batch(hh, pts, offs, nthreads=4)
+    ok = [0, 1, 3, 5, 6]
+    report(f"long scans ragged batch: pose diff {pose_err(P[ok], W[ok])}")
+    check_poses(P[ok], W[ok], "ragged batch of long scans")
+    assert np.array_equal(P[2], hh[2])            # empty scan: pose = hint
+    assert np.all(np.isfinite(P)) and np.all(np.isfinite(C))
+    # the fused converters keep the whole converted scan in shared memory: a cloud that cannot fit is refused, loudly
+    rep.set_cloud_format(synth.laser_transform(), **synth.CLOUD_FORMAT)
+    cloud = np.zeros((40000, 3), np.float32)
+    cloud[:, 0] = np.linspace(1.0, 20.0, 40000, dtype=np.float32)
+    with pytest.raises(capi.HsbError):
+        rep.match_batch_cloud(hints[:1], cloud, np.int32([0, 40000]))
+    got2, _ = rep.matchData(hints[0], longs[0])   # and the handle stays usable
+    assert np.array_equal(got2, got)
+    rep.close()
+    orc.close()
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_non_square_map_other_resolution_and_start(hsb_lib, pyoracle, oracle_kinds, mode):
     """map_size_x != map_size_y, resolution 0.025 (the node's default), start coords off-centre,
