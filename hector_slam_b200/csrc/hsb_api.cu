@@ -83,6 +83,8 @@ struct hsb_handle {
   float* h_pin_dev = nullptr;    // device alias of h_pin
   int shape_batch = 0;           // > 0: pick the launch shape for this batch size instead of the launch's own (pipelined host calls)
   int tune_host_out = 1;         // single-scan calls: kernels write results into mapped host memory (no D2H copy)
+  int tune_inline_scan = 1;      // single-scan calls: the scan travels in the kernel parameters (no H2D copy operation)
+  hsb::InlineScan<true> inline_scan;   // host image of those parameters
   cudaEvent_t ev_time[2] = {nullptr, nullptr};   // timing events around K2 (tuning "time_update")
   int tune_time_update = 0;
   BatchSet bset[2];             // device staging of the host-buffer batch calls, alternating between calls
@@ -234,15 +236,16 @@ void fill_level_dev(const hsb_handle* h, int l, HsbLevelDev& d) {
 }
 
 // ---- match launch -----------------------------------------------------------------------------
-template <int W, int G, int MODE, int U, bool PACK>
-int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int Gr) {
+template <int W, int G, int MODE, int U, bool PACK, bool INL = false>
+int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st, int Gr,
+                   const hsb::InlineScan<INL>& S = hsb::InlineScan<INL>()) {
   if (Gr <= 0 || Gr > G) Gr = G;   // groups per CTA actually launched (a G-group kernel runs with fewer: see launch_match)
   const size_t header = hsb::MatchSmem<W, G>::kHeaderBytes;
-  auto kern = hsb::match_kernel<W, G, MODE, U, PACK>;
+  auto kern = hsb::match_kernel<W, G, MODE, U, PACK, INL>;
   constexpr size_t kMaxDyn = 232448;   // dynamic shared memory one CTA may ask for (227 KB)
   constexpr int gt = W * 32;           // threads per scan
   int cap = 0;
-  const bool fused = P.ranges || P.cloud;   // conversion fused into the staging step: the whole scan must be staged
+  const bool fused = P.ranges || P.cloud || INL;   // conversion / inline scan: the whole scan must be staged
   if (h->tune_stage_smem || fused) cap = ((max_n + 1) + 1) & ~1;  // n + head padding, even
   // resident CTAs per SM for a given dynamic shared-memory size: block, thread, register and
   // shared-memory limits (1 KB per CTA is reserved by the driver)
@@ -311,7 +314,7 @@ int launch_match_t(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st,
   }
   const int seq = h->tune_seq > 0 ? h->tune_seq : 1;  // scans each group handles one after the other
   int grid = (P.B + Gr * seq - 1) / (Gr * seq);
-  kern<<<grid, W * Gr * 32, smem, st>>>(P);
+  kern<<<grid, W * Gr * 32, smem, st>>>(P, S);
   h->launches++;
   {
     const int shape[6] = {W, Gr, U, cap > 0 ? (cap > max_n ? max_n : ((cap - 2) / (W * 32)) * (W * 32)) : 0, grid, resident(smem)};
@@ -389,6 +392,32 @@ int launch_match(hsb_handle* h, HsbMatchParams& P, int max_n, cudaStream_t st) {
   int U = h->tune_unroll > 0 ? h->tune_unroll : 4;
   if (h->gather_mode == HSB_GATHER_TEX) return launch_match_mode<hsb::MODE_TEX>(h, P, max_n, st, W, G, U, Gr);
   return launch_match_mode<hsb::MODE_LDG>(h, P, max_n, st, W, G, U, Gr);
+}
+
+// Single-scan launch with the scan INSIDE the kernel parameters (hsb_match_data, hsb_slam_update; match_kernel.cuh
+// InlineScan): the shape a single scan always takes (8 warps, 4 gathers in flight), so results equal the copy path's.
+bool inline_scan_applies(const hsb_handle* h, int n) {
+  return h->tune_inline_scan && n <= HSB_INLINE_MAX_POINTS && (h->tune_warps_per_scan == 0 || h->tune_warps_per_scan == 8) &&
+         h->tune_scans_per_block <= 1 && (h->tune_unroll == 0 || h->tune_unroll == 4) && !h->tune_packed && h->tune_seq <= 1;
+}
+int launch_match_inline(hsb_handle* h, HsbMatchParams& P, const float* header, int nh, const float* pts, int n, float* d_pts_out,
+                        cudaStream_t st) {
+  hsb::InlineScan<true>& S = h->inline_scan;
+  memset(S.header, 0, sizeof(S.header));
+  if (nh > 0) memcpy(S.header, header, (size_t)nh * sizeof(float));
+  if (n > 0) memcpy(S.pts, pts, (size_t)n * 8);
+  P.B = 1;
+  P.hints = nullptr;
+  P.pts = nullptr;
+  P.offsets = nullptr;
+  P.n_shared = n;
+  P.out_pts = reinterpret_cast<float2*>(d_pts_out);
+  if (h->map_write_pending && st != h->stream) {
+    HSB_CUDA(h, cudaEventRecord(h->ev_sync[0], h->stream));
+    HSB_CUDA(h, cudaStreamWaitEvent(st, h->ev_sync[0], 0));
+  }
+  if (h->gather_mode == HSB_GATHER_TEX) return launch_match_t<8, 1, hsb::MODE_TEX, 4, false, true>(h, P, n, st, 1, S);
+  return launch_match_t<8, 1, hsb::MODE_LDG, 4, false, true>(h, P, n, st, 1, S);
 }
 
 // Copy/compute pipeline of the host-buffer batch calls.  A call of >= 2048 scans travels in TWO halves: the second
@@ -735,6 +764,7 @@ int hsb_set_tuning(hsb_handle* h, const char* key, int value) {
   else if (!strcmp(key, "packed")) h->tune_packed = value;
   else if (!strcmp(key, "seq")) h->tune_seq = value;
   else if (!strcmp(key, "host_out")) h->tune_host_out = value;
+  else if (!strcmp(key, "inline_scan")) h->tune_inline_scan = value;
   else if (!strcmp(key, "partial")) h->tune_partial = value;
   else if (!strcmp(key, "prefetch")) h->tune_prefetch = value;
   else if (!strcmp(key, "trace")) h->tune_trace = value;
@@ -816,7 +846,6 @@ int hsb_match_data(hsb_handle* h, const float hint[3], const float* pts, int n, 
   if (s != HSB_OK) return s;
   float* d_s = static_cast<float*>(h->d_scratch.p);  // [4..6] pose, [8..16] cov
   cudaStream_t st = h->stream;
-  if ((s = upload_scan(h, h->d_last_pts, hint, 3, pts, n, st)) != HSB_OK) return s;   // header [0..2] = hint
   h->last_n = n;
   h->last_origo[0] = origo ? origo[0] : 0.f;
   h->last_origo[1] = origo ? origo[1] : 0.f;
@@ -825,7 +854,19 @@ int hsb_match_data(hsb_handle* h, const float hint[3], const float* pts, int n, 
   const bool host_out = h->tune_host_out != 0;
   float* o_pose = host_out ? h->h_pin_dev + 4 : d_s + 4;
   float* o_cov = host_out ? h->h_pin_dev + 8 : d_s + 8;
-  s = hsb_match_batch_device(h, 1, scan_header(h->d_last_pts), scan_points(h->d_last_pts), nullptr, n, n, o_pose, o_cov, st);
+  if (inline_scan_applies(h, n)) {
+    // ... and the scan goes in with the launch itself: no host-to-device copy operation either; the kernel leaves
+    // the endpoints in d_last_pts for hsb_update_by_scan's coarse levels
+    if ((s = ensure_scan_buf(h, h->d_last_pts, n)) != HSB_OK) return s;
+    HsbMatchParams P;
+    fill_match_params(h, P);
+    P.out_poses = o_pose;
+    P.out_cov = o_cov;
+    s = launch_match_inline(h, P, hint, 3, pts, n, scan_points(h->d_last_pts), st);
+  } else {
+    if ((s = upload_scan(h, h->d_last_pts, hint, 3, pts, n, st)) != HSB_OK) return s;   // header [0..2] = hint
+    s = hsb_match_batch_device(h, 1, scan_header(h->d_last_pts), scan_points(h->d_last_pts), nullptr, n, n, o_pose, o_cov, st);
+  }
   if (s != HSB_OK) return s;
   if (!host_out) HSB_CUDA(h, cudaMemcpyAsync(h->h_pin + 4, d_s + 4, 13 * sizeof(float), cudaMemcpyDeviceToHost, st));
   HSB_CUDA(h, cudaStreamSynchronize(st));
@@ -1435,7 +1476,10 @@ static int slam_update_impl(hsb_handle* h, const float hint[3], const float* pts
   volatile unsigned* seq = reinterpret_cast<volatile unsigned*>(h->h_pin + 22);
   unsigned* seq_dev = reinterpret_cast<unsigned*>(h->h_pin_dev + 22);
   const unsigned seq_value = ++h->step_seq;
-  if ((s = upload_scan(h, pbuf, header, 6, pts, n, st)) != HSB_OK) return s;
+  const bool inl = !map_without_matching && inline_scan_applies(h, n);   // header + scan travel in the match launch
+  if (inl) s = ensure_scan_buf(h, pbuf, n);
+  else s = upload_scan(h, pbuf, header, 6, pts, n, st);
+  if (s != HSB_OK) return s;
   const float* d_hdr = scan_header(pbuf);
   const float* d_pose_in = d_hdr;  // the hint, unless matched below
   if (!map_without_matching) {
@@ -1443,8 +1487,20 @@ static int slam_update_impl(hsb_handle* h, const float hint[3], const float* pts
     h->last_origo[0] = origo ? origo[0] : 0.f;
     h->last_origo[1] = origo ? origo[1] : 0.f;
     // :78 match, and :83-89 the gate in the same kernel's epilogue (an empty scan still passes through it: pose = hint)
-    s = match_device(h, 1, d_hdr, scan_points(pbuf), nullptr, n, n, d_s + 8, host_out ? h->h_pin_dev + 12 : d_s + 12, d_gate,
-                     d_hdr + 3, host_out ? h->h_pin_dev + 8 : nullptr, st, poll ? seq_dev : nullptr, seq_value);
+    if (inl) {
+      HsbMatchParams P;
+      fill_match_params(h, P);
+      P.out_poses = d_s + 8;
+      P.out_cov = host_out ? h->h_pin_dev + 12 : d_s + 12;
+      P.gate_state = d_gate;
+      P.gate_out_host = host_out ? h->h_pin_dev + 8 : nullptr;
+      P.seq_host = poll ? seq_dev : nullptr;
+      P.seq_value = seq_value;
+      s = launch_match_inline(h, P, header, 6, pts, n, scan_points(pbuf), st);
+    } else {
+      s = match_device(h, 1, d_hdr, scan_points(pbuf), nullptr, n, n, d_s + 8, host_out ? h->h_pin_dev + 12 : d_s + 12, d_gate,
+                       d_hdr + 3, host_out ? h->h_pin_dev + 8 : nullptr, st, poll ? seq_dev : nullptr, seq_value);
+    }
     if (s != HSB_OK) return s;
   } else {
     hsb::slam_gate_kernel<<<1, 32, 0, st>>>(d_gate, d_hdr + 3, d_pose_in, d_s + 8, host_out ? h->h_pin_dev + 8 : nullptr,

@@ -693,15 +693,28 @@ struct MatchSmem {
   static constexpr int kHeaderBytes = ((kBarBytes + kRedFloats * 4 + kCntInts * 4 + kProgInts * 4) + 15) / 16 * 16;
 };
 
+// The scan of a single-scan call can travel INSIDE the kernel launch (kernel parameters, up to 32 KB on sm_70+ since
+// CUDA 12.1): [16-float header = hint, gate thresholds | endpoints].  That removes the host-to-device copy operation
+// and the copy-engine -> compute dependency from the critical path of hsb_match_data / hsb_slam_update (measured
+// 7-10 us of a 40 us call, profiles/r02_k1_single_scan.log).  InlineScan<false> is empty: the batch kernels are unchanged.
+#define HSB_INLINE_MAX_POINTS 1280
+template <bool INL>
+struct InlineScan {};
+template <>
+struct InlineScan<true> {
+  float header[16];
+  float2 pts[HSB_INLINE_MAX_POINTS];
+};
+
 // one-warp scans grouped into CTAs: ask for the registers of 28 warps per SM like the G = 1 shape has
 template <int W, int G>
 struct MatchBounds {
   static constexpr int kMinBlocks = (W == 1 && 28 % G == 0) ? 28 / G : 1;
 };
 
-template <int W, int G, int MODE, int U, bool PACK>
+template <int W, int G, int MODE, int U, bool PACK, bool INL = false>
 __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
-    match_kernel(const __grid_constant__ HsbMatchParams P) {
+    match_kernel(const __grid_constant__ HsbMatchParams P, const __grid_constant__ InlineScan<INL> S) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* mbars = reinterpret_cast<uint64_t*>(smem_raw);
   float* red_all = reinterpret_cast<float*>(smem_raw + MatchSmem<W, G>::kBarBytes);
@@ -770,7 +783,18 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
     bool staged = false;
     int ns = 0;                      // points [0, ns) are read from shared memory, [ns, n) from global memory
     if (HSB_DIAG && P.trace && t == 0) P.trace[8 * (size_t)scan] = global_timer_ns();
-    if (P.ranges) {
+    if constexpr (INL) {
+      // the endpoints arrived with the launch: parameter space -> shared memory, and out to device memory for the map
+      // writer and the coarse-level containers of later calls (host guarantees cap >= n, n <= HSB_INLINE_MAX_POINTS)
+      for (int i = t; i < n; i += GT) {
+        const float2 v = S.pts[i];
+        spts[i] = v;
+        if (P.out_pts) P.out_pts[i] = v;
+      }
+      group_sync<W>(g);
+      ns = n;
+      staged = true;
+    } else if (P.ranges) {
       // raw ranges in: convert + compact straight into shared memory (host guarantees cap >= n_beams)
       n = stage_from_ranges<W>(P.ranges + (size_t)scan * P.n_beams, P.beam_cs, P.n_beams, P.range_min, P.range_max_c,
                                P.scale_to_map, spts, warp_cnt, g, w, lane);
@@ -834,7 +858,10 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
     }
     const int npairs = (pack_head + n + 1) >> 1;
 
-    float wx = P.hints[3 * scan + 0], wy = P.hints[3 * scan + 1], wpsi = P.hints[3 * scan + 2];
+    const float* hint;
+    if constexpr (INL) hint = S.header;
+    else hint = P.hints + 3 * scan;
+    float wx = hint[0], wy = hint[1], wpsi = hint[2];
     Acc last;
     acc_zero(last);
     if (n > 0) {
@@ -933,7 +960,10 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
     }
     if (t == 0 && P.gate_state) {
       // fused SLAM step (one scan): the map-update gate runs in the match kernel's epilogue — no separate launch
-      slam_gate(P.gate_state, P.gate_in, wx, wy, wpsi, P.out_poses, P.gate_out_host);
+      const float* gate_in;
+      if constexpr (INL) gate_in = S.header + 3;
+      else gate_in = P.gate_in;
+      slam_gate(P.gate_state, gate_in, wx, wy, wpsi, P.out_poses, P.gate_out_host);
     } else if (t == 0) {
       P.out_poses[3 * scan + 0] = wx;
       P.out_poses[3 * scan + 1] = wy;

@@ -46,4 +46,29 @@ for W, U in ((8, 4), (8, 5), (4, 4), (16, 3), (2, 8)):
     except Exception as e:  # noqa: BLE001
         print(f"W={W} U={U}: {e}", flush=True)
 rep.set_tuning(warps_per_scan=0, scans_per_block=0, unroll=0, trace=0)
+# what the host->device copy of the scan costs the call: the same launch on device-resident inputs, synchronised
+import torch  # noqa: E402
+
+dev = torch.device("cuda", 0)
+d_pts = [torch.from_numpy(s).to(dev) for s in scans]
+d_hints = [torch.from_numpy(np.ascontiguousarray(h)).to(dev) for h in hints]
+d_pose = torch.empty(3, dtype=torch.float32, device=dev)
+d_cov = torch.empty(9, dtype=torch.float32, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+lat = []
+for i in range(220):
+    k = i % 32
+    n = scans[k].shape[0]
+    t0 = time.perf_counter()
+    rep.match_batch_device(1, d_hints[k].data_ptr(), d_pts[k].data_ptr(), None, n, n, d_pose.data_ptr(), d_cov.data_ptr(), st)
+    torch.cuda.current_stream().synchronize()
+    lat.append(time.perf_counter() - t0)
+print(f"hsb_match_batch_device(B=1) + stream synchronize, inputs resident: p50 {np.median(lat[20:]) * 1e6:5.1f} us "
+      f"(hsb_match_data with the copy of the scan: see above)", flush=True)
+lat = []
+for i in range(220):
+    t0 = time.perf_counter()
+    torch.cuda.current_stream().synchronize()
+    lat.append(time.perf_counter() - t0)
+print(f"an empty stream synchronize from Python: p50 {np.median(lat[20:]) * 1e6:5.1f} us", flush=True)
 rep.close()

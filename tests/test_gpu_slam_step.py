@@ -178,3 +178,51 @@ def test_nowait_step_equals_the_synchronous_step(hsb_lib):
     assert any(a[1]) and not all(a[1])
     for l in range(3):
         assert np.array_equal(a[3][l], b[3][l])
+
+
+def test_scan_inside_the_launch_equals_the_copy_path(hsb_lib):
+    """Single-scan calls send the scan inside the kernel parameters (tuning key inline_scan, default on, scans of up to
+    1280 endpoints): poses, covariances, gate decisions and planes of a SLAM run must equal the host-to-device-copy
+    path's bit for bit — through hsb_slam_update (sync and nowait), through hsb_match_data + hsb_update_by_scan (the
+    kernel has to leave the endpoints on the device for the coarse levels), with an empty scan and with a scan too long
+    to be inlined in between."""
+    from hector_slam_b200 import capi
+
+    g = load_golden("slam3.npz")
+    long_scan = np.concatenate([g["scans"][0], g["scans"][1]]).astype(np.float32)   # 2162 endpoints: copy path in both
+
+    def run(inline, mode):
+        rep = capi.MapRepB200(float(g["res"]), int(g["size"]), levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+        rep.set_tuning(inline_scan=inline)
+        rep.setMapUpdateMinDistDiff(0.2)
+        rep.setMapUpdateMinAngleDiff(0.9)
+        hint, out = g["first_hint"], []
+        for k in range(g["scans"].shape[0]):
+            scan = g["scans"][k]
+            if k == 5:
+                scan = long_scan
+            if k == 7:
+                scan = np.zeros((0, 2), np.float32)
+            if mode == "host":
+                p, c = rep.matchData(hint, scan)
+                rep.updateByScan(scan, p)
+                rep.onMapUpdated()
+                out.append((p, c, True))
+            else:
+                p, c, u = rep.slam_update(hint, scan, nowait=(mode == "nowait"))
+                out.append((p, c, u))
+            hint = p
+        rep.onMapUpdated()
+        planes = [rep.download_level(l) for l in range(3)]
+        launches = rep.launch_count
+        rep.close()
+        return out, planes, launches
+
+    for mode in ("sync", "nowait", "host"):
+        a, pa, la = run(1, mode)
+        b, pb, lb = run(0, mode)
+        for k, (x, y) in enumerate(zip(a, b)):
+            assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2], (mode, k, x, y)
+        for l in range(3):
+            assert np.array_equal(pa[l], pb[l]), (mode, l)
+        assert la == lb   # same kernels either way: only the copy operation is gone
