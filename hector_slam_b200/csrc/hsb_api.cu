@@ -83,7 +83,7 @@ struct hsb_handle {
   float* h_pin_dev = nullptr;    // device alias of h_pin
   int shape_batch = 0;           // > 0: pick the launch shape for this batch size instead of the launch's own (pipelined host calls)
   int tune_host_out = 1;         // single-scan calls: kernels write results into mapped host memory (no D2H copy)
-  int tune_inline_scan = 1;      // single-scan calls: the scan travels in the kernel parameters (no H2D copy operation)
+  int tune_inline_scan = 0;      // 1: single-scan calls send the scan in the kernel parameters (no H2D copy operation) — measured slower, see match_kernel.cuh
   hsb::InlineScan<true> inline_scan;   // host image of those parameters
   cudaEvent_t ev_time[2] = {nullptr, nullptr};   // timing events around K2 (tuning "time_update")
   int tune_time_update = 0;

@@ -695,8 +695,12 @@ struct MatchSmem {
 
 // The scan of a single-scan call can travel INSIDE the kernel launch (kernel parameters, up to 32 KB on sm_70+ since
 // CUDA 12.1): [16-float header = hint, gate thresholds | endpoints].  That removes the host-to-device copy operation
-// and the copy-engine -> compute dependency from the critical path of hsb_match_data / hsb_slam_update (measured
-// 7-10 us of a 40 us call, profiles/r02_k1_single_scan.log).  InlineScan<false> is empty: the batch kernels are unchanged.
+// and the copy-engine -> compute dependency from the critical path of hsb_match_data / hsb_slam_update.  Measured
+// (profiles/r02_k1_single_scan.log, tuning key inline_scan): NOT a win — a launch with 12 KB of parameters and the
+// divergent constant-bank reads of the staging loop (+1.6 us in the kernel) cost more than the 8.7 KB copy they
+// replace: pose latency 39.5 vs 37.1 us, whole step 55.1 vs 52.8 us; only the back-to-back rate improves (22.2 k vs
+// 18.8 k scans/s, one stream operation fewer per step).  Kept as an opt-in (default off), bit-identical
+// (tests/test_gpu_slam_step.py).  InlineScan<false> is empty: the batch kernels' SASS is unchanged.
 #define HSB_INLINE_MAX_POINTS 1280
 template <bool INL>
 struct InlineScan {};
