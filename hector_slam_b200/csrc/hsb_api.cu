@@ -1333,10 +1333,19 @@ static int run_update(hsb_handle* h, HsbUpdateParams& P, int max_n) {
   // mark: two warps per beam, four beams per CTA; apply: a fixed one-wave grid sweeping each level's box
   constexpr int TEAM = 2;
   int blocks = (max_n * TEAM + 7) / 8;
-  int cap = h->sm_count * 8;
+  int cap = (h->sm_count * 6) / (P.levels > 0 ? P.levels : 1);   // all levels' CTAs resident at once (6 per SM: its launch bounds)
+  if (cap < 1) cap = 1;
   if (blocks > cap) blocks = cap;
   if (h->tune_time_update) HSB_CUDA(h, cudaEventRecord(h->ev_time[0], st));
-  int sweep = (h->sm_count * 8) / (P.levels > 0 ? P.levels : 1);
+  // (as many CTAs as are resident at once — the register count decides, 6 per SM today — so that the sweep is ONE wave:
+  // the round-1 grid assumed 8 per SM and ran 1.33 waves, profiles/r02_slam_step_ncu.md)
+  static int apply_ctas_per_sm = 0;
+  if (!apply_ctas_per_sm) {
+    int nb = 0;
+    HSB_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, hsb::update_apply_kernel, 256, 0));
+    apply_ctas_per_sm = nb > 0 ? nb : 4;
+  }
+  int sweep = (h->sm_count * apply_ctas_per_sm) / (P.levels > 0 ? P.levels : 1);
   if (sweep < 1) sweep = 1;
   if (h->tune_pdl) {
     // programmatic dependent launch: see pdl_wait() in update_kernel.cuh

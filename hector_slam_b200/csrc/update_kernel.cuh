@@ -358,11 +358,14 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
     }
     if (bx1 >= 0) {
       bx0 = min(bx0, f.x0); by0 = min(by0, f.y0); bx1 = max(bx1, f.x0); by1 = max(by1, f.y0);
-      const volatile int* cur = slot;
-      if (bx0 < cur[1]) atomicMin(slot + 1, bx0);
-      if (by0 < cur[2]) atomicMin(slot + 2, by0);
-      if (bx1 > cur[3]) atomicMax(slot + 3, bx1);
-      if (by1 > cur[4]) atomicMax(slot + 4, by1);
+      // the four current bounds in ONE L2 round trip (a stale value only costs an atomic that changes nothing; read one
+      // by one through a volatile pointer they were four dependent round trips at the end of every CTA — a third of
+      // this kernel's stall samples, profiles/r02_slam_step_ncu.md)
+      const int c1 = __ldcg(slot + 1), c2 = __ldcg(slot + 2), c3 = __ldcg(slot + 3), c4 = __ldcg(slot + 4);
+      if (bx0 < c1) atomicMin(slot + 1, bx0);
+      if (by0 < c2) atomicMin(slot + 2, by0);
+      if (bx1 > c3) atomicMax(slot + 3, bx1);
+      if (by1 > c4) atomicMax(slot + 4, by1);
     }
   }
 }
