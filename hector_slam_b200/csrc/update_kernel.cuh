@@ -217,10 +217,8 @@ struct BeamFrame {
   int x0, y0;
   bool ok;
 };
-__device__ __forceinline__ BeamFrame beam_frame(const HsbUpdateParams& P, const HsbUpdateLevelDev& L) {
+__device__ __forceinline__ BeamFrame beam_frame(const HsbUpdateLevelDev& L, float wx, float wy, float wpsi) {
   BeamFrame f;
-  const float* pw = P.pose_dev ? P.pose_dev : P.pose_world;
-  const float wx = pw[0], wy = pw[1], wpsi = pw[2];
   const float* m = L.mtw;
   f.mx = __fadd_rn(__fmul_rn(m[0], wx), __fadd_rn(__fmul_rn(m[1], wy), m[2]));
   f.my = __fadd_rn(__fmul_rn(m[3], wx), __fadd_rn(__fmul_rn(m[4], wy), m[5]));
@@ -276,20 +274,26 @@ __global__ void __launch_bounds__(256) update_mark_kernel(const __grid_constant_
   pdl_wait();
   const HsbUpdateLevelDev& L = P.lv[blockIdx.y];
   if (!L.active) return;
-  if (P.gate_flag && *P.gate_flag == 0.0f) return;
+  // gate flag, pose and beam count in ONE L2 round trip (independent loads, issued before the first dependent branch)
+  // (plain loads: every thread reads these words, they have to hit L1)
+  const float flag = P.gate_flag ? *P.gate_flag : 1.0f;
+  const float* pw = P.pose_dev ? P.pose_dev : P.pose_world;
+  const float wx = pw[0], wy = pw[1], wpsi = pw[2];
+  const int n_dev = L.n_dev ? *L.n_dev : L.n;
+  if (flag == 0.0f) return;
   constexpr int TL = 32 * TEAM;   // lanes per team
   constexpr int U = 4;
   const unsigned tlane = threadIdx.x % TL;
   const int team0 = (blockIdx.x * blockDim.x + threadIdx.x) / TL;
   const int team_stride = (gridDim.x * blockDim.x) / TL;
-  const BeamFrame f = beam_frame(P, L);
+  const BeamFrame f = beam_frame(L, wx, wy, wpsi);
   if (!f.ok) return;
   const unsigned start = (unsigned)f.y0 * (unsigned)L.sx + (unsigned)f.x0;
   const uint32_t free_s = L.stamp_base + 1u, occ_s = L.stamp_base + 2u;
   int* slot = L.scratch + 8 * L.slot;
   int bx0 = INT_MAX, by0 = INT_MAX, bx1 = -1, by1 = -1;
 
-  const int n_beams = L.n_dev ? min(*L.n_dev, L.n) : L.n;
+  const int n_beams = min(n_dev, L.n);
   for (int b = team0; b < n_beams; b += team_stride) {
     int x1, y1;
     if (!beam_end(L, f, b, x1, y1)) continue;
@@ -404,8 +408,11 @@ __global__ void __launch_bounds__(256) update_apply_kernel(const __grid_constant
     nxt[0] = 0;
     nxt[1] = INT_MAX; nxt[2] = INT_MAX; nxt[3] = -1; nxt[4] = -1;
   }
-  if (P.gate_flag && *P.gate_flag == 0.0f) return;
+  // gate flag and box in ONE round trip (independent loads, issued before the first dependent branch; plain loads:
+  // every thread of the grid reads these words, they have to hit L1 — ld.cg here cost 2.5 us of L2 hot-spotting)
+  const float flag = P.gate_flag ? *P.gate_flag : 1.0f;
   const int bx0 = cur[1], by0 = cur[2], bx1 = cur[3], by1 = cur[4];
+  if (flag == 0.0f) return;
   if (bx1 < bx0) return;                       // nothing was marked (pose outside the map, every beam dropped)
   if (blockIdx.x == 0 && threadIdx.x == 0 && L.dirty) {   // both rectangles: replication [0..3] and host mirror [4..7]
     atomicMin(L.dirty + 0, bx0); atomicMin(L.dirty + 4, bx0);
