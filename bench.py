@@ -789,6 +789,7 @@ def extra_config5(torch, dist, capi, synth, parallel, new_rep, rank, world_size,
     out = {"workload": "4096 independent 1081-pt scans per GPU per step, 3-level 8192^2 map (1.4 GB of planes, 336 MB of "
                        "probabilities: larger than L2), full matchData", "n_gpus": world_size,
            "value": world_size * B * 10 / (span_ms * 1e-3), "unit": "scan-matches/s", "kernel_ms": kernel_ms,
+           "seconds_per_1M_scans_at_this_rate": 1e6 / (world_size * B * 10 / (span_ms * 1e-3)),
            "roofline": {"bound": "l1tex+l2", "achieved": BYTES_PER_MATCH * B / (kernel_ms * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": BYTES_PER_MATCH * B / (kernel_ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                         "dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
