@@ -171,5 +171,84 @@ HSB_HD void sincosf_glibc(float y, float* sp, float* cp) {
   *cp = (float)cos(x);
 }
 
+// ---- expf as glibc 2.39's x86-64 FMA build evaluates it (sysdeps/ieee754/flt-32/e_expf.c, exp2f_data.c) -----------------
+// Why: the reference turns log-odds into the probability the matcher interpolates with
+// `float odds = exp(l); return odds / (odds + 1.0f)` (GridMapLogOdds.h:165-166; exp(float) resolves to expf).  glibc's
+// expf is accurate to 0.502 ulp, not correctly rounded: a correctly rounded exp differs from it by one ulp on ~1 % of
+// the arguments, i.e. on that share of the cells of a probability plane.  With this restatement the plane is the
+// reference's bit for bit.  Operation order transcribed from the disassembly of __expf_fma (libm.so.6 2.39-0ubuntu8.5):
+//   kd = fma(InvLn2N, x, SHIFT); ki = bits(kd); kd -= SHIFT; r = fma(InvLn2N, x, -kd);
+//   s = asdouble(T[ki % 32] + (ki << 47)); z = fma(r, C0, C1); r2 = r * r; y = fma(r, C2, 1); y = fma(z, r2, y); return (float)(y * s)
+// constants and the 2^(i/32) table read from that library's __exp2f_data.  Out-of-range arguments as glibc handles them:
+// NaN / +inf -> x + x, x > 0x1.62e42ep6 -> +inf, x < -0x1.9fe368p6 -> +0, x < -0x1.9d1d9ep6 -> 0x1.4p-75f squared (= 2^-149).
+// tests/test_sincosf_glibc.py checks the host build against the running libm bit for bit.
+#define HSB_EXPF_SHIFT 0x1.8p+52
+#define HSB_EXPF_INVLN2N 0x1.71547652b82fep+5
+#define HSB_EXPF_C0 0x1.c6af84b912394p-20
+#define HSB_EXPF_C1 0x1.ebfce50fac4f3p-13
+#define HSB_EXPF_C2 0x1.62e42ff0c52d6p-6
+
+#define HSB_EXP2F_TABLE \
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, \
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, \
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull, \
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull, \
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull, \
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull, \
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, \
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
+static const unsigned long long hsb_exp2f_table_host[32] = {HSB_EXP2F_TABLE};
+#if defined(__CUDACC__)
+// (global, not __constant__ memory: the index differs from lane to lane, and divergent constant-bank reads serialise)
+__device__ const unsigned long long hsb_exp2f_table_dev[32] = {HSB_EXP2F_TABLE};
+#endif
+
+HSB_HD float expf_glibc(float x) {
+  const uint32_t ux = f32_bits(x);
+  const uint32_t abstop = (ux >> 20) & 0x7ffu;
+  if (abstop > 0x42au) {   // |x| >= 88 or NaN
+    if (ux == 0xff800000u) return 0.0f;
+    if (abstop >= 0x7f8u) return x + x;
+    if (x > 0x1.62e42ep6f) return INFINITY;
+    if (x < -0x1.9fe368p6f) return 0.0f;
+    if (x < -0x1.9d1d9ep6f) {
+#if defined(__CUDA_ARCH__)
+      return __uint_as_float(1u);   // 0x1.4p-75f * 0x1.4p-75f rounds to the smallest denormal
+#else
+      volatile float tiny = 0x1.4p-75f;
+      return tiny * tiny;
+#endif
+    }
+  }
+  const double xd = (double)x;
+  double kd = HSB_DFMA(HSB_EXPF_INVLN2N, xd, HSB_EXPF_SHIFT);
+  uint64_t ki;
+#if defined(__CUDA_ARCH__)
+  ki = (uint64_t)__double_as_longlong(kd);
+  kd = __dadd_rn(kd, -HSB_EXPF_SHIFT);
+#else
+  memcpy(&ki, &kd, 8);
+  kd = kd - HSB_EXPF_SHIFT;
+#endif
+  const double r = HSB_DFMA(HSB_EXPF_INVLN2N, xd, -kd);
+#if defined(__CUDA_ARCH__)
+  const uint64_t t = (uint64_t)hsb_exp2f_table_dev[ki & 31u] + (ki << 47);
+#else
+  const uint64_t t = (uint64_t)hsb_exp2f_table_host[ki & 31u] + (ki << 47);
+#endif
+  double s;
+#if defined(__CUDA_ARCH__)
+  s = __longlong_as_double((long long)t);
+#else
+  memcpy(&s, &t, 8);
+#endif
+  const double z = HSB_DFMA(r, HSB_EXPF_C0, HSB_EXPF_C1);
+  const double r2 = HSB_DMUL(r, r);
+  double y = HSB_DFMA(r, HSB_EXPF_C2, 1.0);
+  y = HSB_DFMA(z, r2, y);
+  y = HSB_DMUL(y, s);
+  return (float)y;
+}
+
 }  // namespace hsb
 #endif

@@ -32,10 +32,11 @@
 
 namespace hsb {
 
-// P = e^l / (e^l + 1) in fp32 like the reference (expf, then one division).  exp is evaluated in
-// double and rounded once, which reproduces a correctly rounded expf (glibc's is, to 0.502 ulp).
+// P = e^l / (e^l + 1) in fp32 like the reference (GridMapLogOdds.h:165-166: expf, one addition, one division).  expf is
+// glibc's, operation for operation (sincosf_glibc.h: expf_glibc) — a correctly rounded exp differs from it by one ulp on
+// ~1 % of the arguments — so the probability plane equals the reference's bit for bit.
 __device__ __forceinline__ float prob_from_logodds(float l) {
-  const float odds = (float)exp((double)l);
+  const float odds = expf_glibc(l);
   return __fdiv_rn(odds, __fadd_rn(odds, 1.0f));
 }
 

@@ -69,9 +69,37 @@ def test_probability_plane(hsb_lib, mode):
         rep.upload_level(l, g[f"plane{l}"])
         assert np.array_equal(rep.download_level(l), g[f"plane{l}"])
         got, want = rep.download_prob(l), g[f"prob{l}"]
-        assert np.abs(got - want).max() <= 6e-8  # one ulp of a probability in (0.5, 1]
-        assert (got != want).mean() < 0.02       # and identical almost everywhere
+        assert np.array_equal(got, want)         # expf as glibc evaluates it (sincosf_glibc.h): bit for bit
     rep.close()
+
+
+def test_probability_plane_whole_range(hsb_lib, pyoracle, oracle_kinds):
+    """Every log-odds value a cell can reach — the free side is not clamped, so long runs go far below expf's underflow
+    thresholds (-103.28, -103.97), the occupied side stops at 50 + lo — against getGridProbability of the compiled
+    reference, bit for bit."""
+    from hector_slam_b200 import capi
+
+    kind = "reference" if "reference" in oracle_kinds else "port"
+    size = 512
+    rng = np.random.default_rng(11)
+    plane = np.empty((size, size), np.float32)
+    plane[:128] = rng.uniform(-120.0, 52.2, (128, size))
+    plane[128:256] = rng.uniform(-104.2, -103.0, (128, size))          # around the underflow thresholds
+    lf, lo = np.float32(np.log(np.float32(0.4) / np.float32(0.6))), np.float32(np.log(np.float32(0.9) / np.float32(0.1)))
+    acc = np.zeros(size, np.float32)
+    for r in range(256, 384):                                           # accumulated exactly like a cell: k free steps
+        acc = (acc + lf).astype(np.float32)
+        plane[r] = acc
+    plane[384:] = (rng.integers(0, 30, (128, size)).astype(np.float32) * lo + rng.integers(0, 300, (128, size)).astype(np.float32) * lf)
+    plane[0, :8] = [0.0, -0.0, 50.0, 52.197224, -103.27893, -103.97208, -1e30, 88.0]
+    orc = pyoracle.Oracle(kind, 0.05, size, 1)
+    orc.set_logodds(0, plane)
+    rep = capi.MapRepB200(0.05, size, levels=1)
+    rep.upload_level(0, plane)
+    got, want = rep.download_prob(0), orc.get_prob(0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), int((got != want).sum())
+    rep.close()
+    orc.close()
 
 
 @pytest.mark.parametrize("mode", MODES)
