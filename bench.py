@@ -621,12 +621,14 @@ def main():
             "clocks": clocks,
             "wall_ms_per_step": 1e3 * (t_wall1 - t_wall0) / (args.steps + args.warmup),
         }
+        line.update(extras)
+        if world_size == 1 and not args.no_extras:
+            # (latencies of single calls: taken BEFORE the 128-thread CPU baseline below, whose aftermath on the host
+            # cores otherwise adds ~3 us to every call)
+            line.update(extra_config3(capi, synth, new_rep, args))
         if not args.no_cpu_baseline and world_size == 1:
             _, info = cpu_reference_run(pts, offs, hints, planes_host, steps=3, warmup=1, max_seconds=16.0)
             line["cpu_baseline"] = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        line.update(extras)
-        if world_size == 1 and not args.no_extras:
-            line.update(extra_config3(capi, synth, new_rep, args))
     rep.close()
     if world_size > 1:
         dist.barrier()
