@@ -705,20 +705,18 @@ def extra_config4(torch, dist, capi, synth, parallel, new_rep, rank, world_size,
     stream = torch.cuda.current_stream().cuda_stream
     best = {}
 
-    d_score = torch.empty(n, dtype=torch.float32, device=dev)
+    mine_best = torch.empty(4, dtype=torch.float32, device=dev)
 
     def step(i):
         rep.match_batch_device(n, d_hyp.data_ptr(), d_scan.data_ptr(), None, scan.shape[0], scan.shape[0], d_out.data_ptr(),
                                None, stream)
         if i < 0:
             return
-        # score + arg-max across ranks (the exchange step of this config): likelihood of every matched pose on level 0,
-        # computed where the poses lie (hsb_likelihood_batch_device), arg-max on the device, ONE all-gather of
-        # (score, pose) per step and one 16-byte-per-rank read by the host
-        rep.likelihood_batch_device(0, n, d_out.data_ptr(), d_scan.data_ptr(), None, scan.shape[0], d_score.data_ptr(), stream)
-        score = torch.where(torch.isfinite(d_out).all(dim=1), d_score, torch.full_like(d_score, -1.0))
-        k = torch.argmax(score)
-        mine_best = torch.cat([score[k].reshape(1), d_out[k]])
+        # score + arg-max across ranks (the exchange step of this config): likelihood of every matched pose on level 0
+        # with the arg-max folded in (hsb_best_hypothesis_device: two launches), ONE all-gather of (score, pose) per
+        # step and one 16-byte-per-rank read by the host
+        rep.best_hypothesis_device(0, n, d_out.data_ptr(), d_scan.data_ptr(), None, scan.shape[0], mine_best.data_ptr(),
+                                   None, stream)
         if world_size > 1:
             allb = torch.empty((world_size, 4), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(allb, mine_best)
@@ -749,7 +747,7 @@ def extra_config4(torch, dist, capi, synth, parallel, new_rep, rank, world_size,
     return {"config4_relocalisation": {
         "workload": "65 536 pose hypotheses x one 1081-pt scan, fixed 3-level 4096^2 map, sharded over the ranks",
         "scaling": "strong", "n_gpus": world_size, "hypotheses_per_gpu": n,
-        "value": H * steps / float(te.item()), "unit": "hypotheses/s (match + likelihood score on the device + arg-max all-gather; the host reads the winner every step)",
+        "value": H * steps / float(te.item()), "unit": "hypotheses/s (match + likelihood score with fused arg-max on the device + all-gather; the host reads the winner every step)",
         "match_kernel_only": H * 5 / (span_ms * 1e-3), "ms_per_step": 1e3 * float(te.item()) / steps,
         "best_hypothesis_error_m": err, "collective": "all_gather of 4 floats per rank per step" if world_size > 1 else "none"}}
 

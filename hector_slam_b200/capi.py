@@ -28,7 +28,7 @@ EXPORTED = [
     "hsb_upload_level", "hsb_download_level", "hsb_download_prob", "hsb_level_logodds_device_ptr",
     "hsb_refresh_level", "hsb_last_error", "hsb_status_string", "hsb_get_launch_count", "hsb_get_gather_mode",
     "hsb_set_tuning", "hsb_version", "hsb_set_scan_format", "hsb_scan_to_points", "hsb_match_batch_ranges",
-    "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch", "hsb_likelihood_batch_device",
+    "hsb_match_batch_ranges_device", "hsb_download_occupancy", "hsb_likelihood_batch", "hsb_likelihood_batch_device", "hsb_best_hypothesis_device",
     "hsb_get_dirty_rect", "hsb_pack_rect_device", "hsb_unpack_rect_device", "hsb_raycast_batch",
     "hsb_read_trace", "hsb_get_last_launch_shape", "hsb_get_last_update_device_ms",
     "hsb_match_batch_submit", "hsb_match_batch_ranges_submit", "hsb_match_batch_cloud_submit", "hsb_match_batch_wait",
@@ -133,6 +133,7 @@ def load_library() -> C.CDLL:
     sig("hsb_download_occupancy", i, vp, i, vp)
     sig("hsb_likelihood_batch", i, vp, i, i, vp, vp, vp, i, vp)
     sig("hsb_likelihood_batch_device", i, vp, i, i, vp, vp, vp, i, vp, vp)
+    sig("hsb_best_hypothesis_device", i, vp, i, i, vp, vp, vp, i, vp, vp, vp)
     sig("hsb_covariance_batch", i, vp, i, i, vp, vp, vp, i, vp, vp)
     sig("hsb_get_map_origin", i, vp, i, vp)
     sig("hsb_get_dist_batch", i, vp, i, i, vp, vp, vp, vp, vp)
@@ -597,6 +598,12 @@ class MapRepB200:
         """getLikelihoodForState on device pointers, enqueued on `stream` (no synchronisation)."""
         self._check(self.lib.hsb_likelihood_batch_device(self.h, level, B, d_poses_world, d_points_xy, d_offsets, n_shared,
                                                          d_out, stream))
+
+    def best_hypothesis_device(self, level: int, B: int, d_poses_world: int, d_points_xy: int, d_offsets, n_shared: int,
+                               d_best4: int, d_out=None, stream: int = 0) -> None:
+        """likelihood of B poses + arg-max on the device: d_best4 <- {likelihood, x, y, psi} of the best one."""
+        self._check(self.lib.hsb_best_hypothesis_device(self.h, level, B, d_poses_world, d_points_xy, d_offsets, n_shared,
+                                                        d_out, d_best4, stream))
 
     def covariance_batch(self, level: int, poses_world, points_xy, offsets=None):
         """getCovarianceForPose (+ getCovMatrixWorldCoords) for B world poses. -> (cov_map (B,3,3), cov_world (B,3,3))"""

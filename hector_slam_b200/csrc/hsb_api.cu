@@ -97,6 +97,7 @@ struct hsb_handle {
   // tuning
   int tune_warps_per_scan = 0, tune_scans_per_block = 0, tune_stage_smem = 1, tune_chunk = 0, tune_unroll = 0, tune_packed = 0, tune_seq = 0, tune_partial = 1, tune_prefetch = 0, tune_trace = 0, tune_pace = 0, tune_pdl = 1, tune_auto_group = 1, tune_stagger = 0;
   DevBuf d_trace;
+  DevBuf d_best;   // arg-max accumulator of hsb_best_hypothesis_device
   bool map_write_pending = false;   // a nowait SLAM step's map write may still be running on `stream`
   unsigned step_seq = 0;   // sequence number of the fused SLAM steps (host polling, hsb_slam_update_nowait)
   int trace_scans = 0;
@@ -657,7 +658,7 @@ int hsb_destroy(hsb_handle* h) {
   cudaDeviceSynchronize();
   for (int l = 0; l < HSB_MAX_LEVELS; ++l) destroy_level(h, h->lv[l]);
   DevBuf* bufs[] = {&h->d_hints, &h->d_pts, &h->d_offsets, &h->d_poses, &h->d_cov, &h->d_scratch, &h->d_gate, &h->d_last_pts, &h->d_upd_pts,
-                    &h->d_beam_cs, &h->d_ranges, &h->d_occ, &h->d_trace,
+                    &h->d_beam_cs, &h->d_ranges, &h->d_occ, &h->d_trace, &h->d_best,
                     &h->d_cloud, &h->d_cloud_off, &h->d_cloud_tf, &h->d_origo, &h->d_cloud1};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -1816,7 +1817,7 @@ int hsb_download_occupancy(hsb_handle* h, int level, int8_t* out) {
 
 // the likelihood launch on device pointers; `st` may be a caller's stream (ordered behind a pending map write)
 static int likelihood_device(hsb_handle* h, int level, int B, const float* d_poses, const float2* d_pts, const int* d_off,
-                             int n_shared, float* d_out, cudaStream_t st) {
+                             int n_shared, float* d_out, cudaStream_t st, unsigned long long* d_best = nullptr) {
   if (h->map_write_pending && st != h->stream) {
     HSB_CUDA(h, cudaEventRecord(h->ev_sync[0], h->stream));
     HSB_CUDA(h, cudaStreamWaitEvent(st, h->ev_sync[0], 0));
@@ -1825,9 +1826,9 @@ static int likelihood_device(hsb_handle* h, int level, int B, const float* d_pos
   fill_level_dev(h, level, L);
   int blocks = std::min((B + 3) / 4, h->sm_count * 16);
   if (h->gather_mode == HSB_GATHER_TEX)
-    hsb::likelihood_kernel<hsb::MODE_TEX><<<blocks, 128, 0, st>>>(L, B, d_poses, d_pts, d_off, d_off ? 0 : n_shared, d_out);
+    hsb::likelihood_kernel<hsb::MODE_TEX><<<blocks, 128, 0, st>>>(L, B, d_poses, d_pts, d_off, d_off ? 0 : n_shared, d_out, d_best);
   else
-    hsb::likelihood_kernel<hsb::MODE_LDG><<<blocks, 128, 0, st>>>(L, B, d_poses, d_pts, d_off, d_off ? 0 : n_shared, d_out);
+    hsb::likelihood_kernel<hsb::MODE_LDG><<<blocks, 128, 0, st>>>(L, B, d_poses, d_pts, d_off, d_off ? 0 : n_shared, d_out, d_best);
   h->launches++;
   HSB_CUDA(h, cudaGetLastError());
   return HSB_OK;
@@ -1842,6 +1843,27 @@ int hsb_likelihood_batch_device(hsb_handle* h, int level, int B, const float* d_
   DeviceGuard guard(h->device);
   return likelihood_device(h, level, B, d_poses_world, reinterpret_cast<const float2*>(d_points_xy), d_offsets, n_shared,
                            d_out_likelihood, (cudaStream_t)stream);
+}
+
+int hsb_best_hypothesis_device(hsb_handle* h, int level, int B, const float* d_poses_world, const float* d_points_xy,
+                               const int* d_offsets, int n_shared, float* d_out_likelihood, float* d_best4, void* stream) {
+  if (!h || level < 0 || level >= h->levels || B < 0 || !d_best4 || (B > 0 && !d_poses_world)) return HSB_ERR_INVALID_ARG;
+  if (!d_offsets && n_shared < 0) return HSB_ERR_INVALID_ARG;
+  if (B > 0 && !d_points_xy && (d_offsets || n_shared > 0)) return fail(h, HSB_ERR_INVALID_ARG, "points pointer is NULL");
+  DeviceGuard guard(h->device);
+  int s;
+  if (!h->d_best.p) {
+    if ((s = ensure(h, h->d_best, sizeof(unsigned long long))) != HSB_OK) return s;
+    HSB_CUDA(h, cudaMemsetAsync(h->d_best.p, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  }
+  unsigned long long* d_best = static_cast<unsigned long long*>(h->d_best.p);
+  if (B > 0 && (s = likelihood_device(h, level, B, d_poses_world, reinterpret_cast<const float2*>(d_points_xy), d_offsets, n_shared,
+                                      d_out_likelihood, (cudaStream_t)stream, d_best)) != HSB_OK)
+    return s;
+  hsb::best_hypothesis_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_best, d_poses_world, d_best4);
+  h->launches++;
+  HSB_CUDA(h, cudaGetLastError());
+  return HSB_OK;
 }
 
 int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses, const float* pts, const int* offsets,

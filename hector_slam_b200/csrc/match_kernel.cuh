@@ -1035,7 +1035,8 @@ __device__ __forceinline__ float warp_likelihood(const LevelRegs& LR, float pt_s
 template <int MODE>
 __global__ void __launch_bounds__(128)
     likelihood_kernel(const HsbLevelDev L, int B, const float* __restrict__ poses_world, const float2* __restrict__ pts_all,
-                      const int* __restrict__ offsets, int n_shared, float* __restrict__ out) {
+                      const int* __restrict__ offsets, int n_shared, float* __restrict__ out,
+                      unsigned long long* __restrict__ best = nullptr) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1049,8 +1050,36 @@ __global__ void __launch_bounds__(128)
     float ex, ey;
     affine_apply_exact(L.mtw, poses_world[3 * b], poses_world[3 * b + 1], ex, ey);
     const float lh = warp_likelihood<MODE>(LR, L.pt_scale, pts_all + beg, n, ex, ey, poses_world[3 * b + 2], lane);
-    if (lane == 0) out[b] = lh;
+    if (lane == 0) {
+      if (out) out[b] = lh;
+      if (best) {
+        // arg-max over the batch (relocalisation: the most likely hypothesis): (score, index) packed so that one
+        // 64-bit atomicMax keeps the highest score and, among equals, the LOWEST index; a non-finite pose scores -1
+        const float px = poses_world[3 * b], py = poses_world[3 * b + 1], pp = poses_world[3 * b + 2];
+        const bool finite = fabsf(px) <= 3.4e38f && fabsf(py) <= 3.4e38f && fabsf(pp) <= 3.4e38f;
+        const float sc = finite ? lh : -1.0f;
+        unsigned u = __float_as_uint(sc);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        atomicMax(best, ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)b));
+      }
+    }
   }
+}
+// second launch of hsb_best_hypothesis_device: unpack the winner, re-arm the accumulator
+__global__ void best_hypothesis_finish_kernel(unsigned long long* __restrict__ best, const float* __restrict__ poses_world,
+                                              float* __restrict__ out4) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long v = *best;
+  *best = 0ull;
+  if (v == 0ull) {   // empty batch
+    out4[0] = -1.0f; out4[1] = 0.0f; out4[2] = 0.0f; out4[3] = 0.0f;
+    return;
+  }
+  unsigned u = (unsigned)(v >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  const unsigned b = 0xffffffffu - (unsigned)(v & 0xffffffffull);
+  out4[0] = __uint_as_float(u);
+  out4[1] = poses_world[3 * b]; out4[2] = poses_world[3 * b + 1]; out4[3] = poses_world[3 * b + 2];
 }
 
 // N3: OccGridMapUtil::getCovarianceForPose (OccGridMapUtil.h:106-160) + getCovMatrixWorldCoords (:162-187) for a batch of

@@ -347,6 +347,12 @@ int hsb_likelihood_batch(hsb_handle* h, int level, int B, const float* poses_wor
  * arg-max without a host round trip.  Same values as the host call. */
 int hsb_likelihood_batch_device(hsb_handle* h, int level, int B, const float* d_poses_world, const float* d_points_xy,
                                 const int* d_offsets, int n_shared, float* d_out_likelihood, void* stream);
+/* Score AND pick (Monte-Carlo relocalisation, BASELINE config 4): the likelihood launch above with an arg-max folded
+ * in — d_best4 receives {likelihood, x, y, psi} of the most likely pose of the batch (lowest index among equals; a
+ * non-finite pose scores -1; an empty batch gives likelihood -1).  d_out_likelihood may be NULL.  Two launches on
+ * `stream`, nothing is synchronised: a multi-GPU caller all-gathers the 16 bytes. */
+int hsb_best_hypothesis_device(hsb_handle* h, int level, int B, const float* d_poses_world, const float* d_points_xy,
+                               const int* d_offsets, int n_shared, float* d_out_likelihood, float* d_best4, void* stream);
 
 /* OccGridMapUtil::getCovarianceForPose — map/OccGridMapUtil.h:106-160 — the sigma-point covariance of a pose: the
  * likelihoods (above) of the pose and of six neighbours (+-1.5 cells in x / y, +-0.05 rad) weight a mean and a 3x3

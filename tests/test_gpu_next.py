@@ -76,6 +76,31 @@ def test_likelihood_batch(hsb_lib, pyoracle, oracle_kinds, mode):
     rep.likelihood_batch_device(0, 3, d_hyp.data_ptr(), d_scan.data_ptr(), None, g["scans"].shape[1], d_sc.data_ptr(), 0)
     torch.cuda.synchronize()
     assert np.array_equal(d_sc.cpu().numpy(), sc)
+    # score + arg-max in one call (relocalisation): the winner of hsb_best_hypothesis_device is numpy's arg-max of the
+    # host call's scores (first index among equals), a non-finite pose never wins, the accumulator re-arms itself
+    rng = np.random.default_rng(4)
+    many = np.repeat(g["ref_poses"][0][None], 300, axis=0).astype(np.float32)
+    many[:, :2] += rng.uniform(-0.3, 0.3, (300, 2)).astype(np.float32)
+    many[17] = many[203] = g["ref_poses"][0]          # two equal best candidates: the first one has to win
+    many[5] = [np.nan, 0.0, 0.0]
+    many[6] = [np.inf, 0.0, 0.0]
+    ok = np.all(np.isfinite(many), axis=1)
+    sc_all = np.full(300, -1.0, np.float32)
+    sc_all[ok] = rep.likelihood_batch(0, many[ok], g["scans"][0], None)
+    d_many = torch.from_numpy(many).to(dev)
+    d_best = torch.zeros(4, dtype=torch.float32, device=dev)
+    d_all = torch.empty(300, dtype=torch.float32, device=dev)
+    for rep_i in range(2):
+        rep.best_hypothesis_device(0, 300, d_many.data_ptr(), d_scan.data_ptr(), None, g["scans"].shape[1], d_best.data_ptr(),
+                                   d_all.data_ptr(), 0)
+        torch.cuda.synchronize()
+        k = int(np.argmax(sc_all))
+        got = d_best.cpu().numpy()
+        assert got[0] == sc_all[k] and np.array_equal(got[1:], many[k]), (rep_i, k, got)
+        assert np.array_equal(d_all.cpu().numpy()[ok], sc_all[ok])
+    rep.best_hypothesis_device(0, 0, d_many.data_ptr(), d_scan.data_ptr(), None, g["scans"].shape[1], d_best.data_ptr(), None, 0)
+    torch.cuda.synchronize()
+    assert d_best.cpu().numpy()[0] == -1.0           # empty batch
     rep.close()
     orc.close()
 
