@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(W * G * 32, MatchBounds<W, G>::kMinBlocks)
   if (P.gate_state) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (t == 0) mbar_init(mbar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  // Pacing (G > 1, P.pace_slack > 0).  Measured with the per-scan timeline (profiles/r02_k1_timeline.md): the warps of
+  // Pacing (G > 1, P.pace_slack > 0).  Measured with the per-scan timeline (profiles/r02_k1_timeline_before.log): the warps of
   // an SM do NOT advance at the same rate — of 28 identical one-warp scans started together the first finishes after
   // 95 us, the last after 142 us — so a one-wave batch ends with a long, thinly occupied tail.  Groups of one CTA
   // therefore publish how many evaluations they have completed and a group that is more than `pace_slack` ahead of
