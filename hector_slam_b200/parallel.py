@@ -209,7 +209,7 @@ def broadcast_dirty_tiles_async(rep, buf: torch.Tensor, src: int = 0, group=None
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     nbytes = buf.numel() * 4
-    stream = torch.cuda.current_stream(buf.device).cuda_stream
+    stream = torch.cuda.current_stream(buf.device).cuda_stream if buf.is_cuda else 0   # (CPU tensors: the gloo tests)
     if dist.get_rank(group) == src:
         rep.pack_dirty_device(buf.data_ptr(), nbytes, True, stream)
     dist.broadcast(buf, src=src, group=group)

@@ -70,6 +70,8 @@ def _worker(rank, world, port, q):
         # dirty-tile protocol with a host stand-in for the handle (same method names as capi.MapRepB200)
         import ctypes
 
+        MAGIC, HDR = 0x48534254, 64   # one-shot buffer: header words of hsb_pack_dirty_device
+
         class FakeRep:
             def __init__(self):
                 self.planes = [np.zeros((32 >> l, 32 >> l), np.float32) for l in range(2)]
@@ -103,6 +105,41 @@ def _worker(rank, world, port, q):
                 n = (x1 - x0 + 1) * (y1 - y0 + 1)
                 self.planes[l][y0:y1 + 1, x0:x1 + 1] = self._view(ptr, n).reshape(y1 - y0 + 1, x1 - x0 + 1)
 
+            # one-shot protocol: the self-describing buffer of hsb_pack_dirty_device / hsb_unpack_dirty_device
+            # (header of 64 words: magic, levels, overflow flag, cells, then x0 y0 x1 y1 per level; rows back to back)
+            def pack_dirty_device(self, ptr, nbytes, reset, stream=0):
+                words = self._view(ptr, nbytes // 4)
+                hdr = words[:HDR].view(np.int32)
+                rects = [self.dirty[l] if self.dirty[l] is not None else (2 ** 31 - 1, 2 ** 31 - 1, -1, -1) for l in range(2)]
+                cells = sum((r[2] - r[0] + 1) * (r[3] - r[1] + 1) for r in rects if r[2] >= r[0])
+                overflow = cells + HDR > nbytes // 4
+                hdr[:4] = [MAGIC, 2, int(overflow), cells]
+                hdr[4:12] = np.int32(rects).reshape(-1)
+                if overflow:
+                    return
+                o = HDR
+                for l, (x0, y0, x1, y1) in enumerate(rects):
+                    if x1 >= x0:
+                        n = (x1 - x0 + 1) * (y1 - y0 + 1)
+                        words[o:o + n] = self.planes[l][y0:y1 + 1, x0:x1 + 1].reshape(-1)
+                        o += n
+                if reset:
+                    self.dirty = [None, None]
+
+            def unpack_dirty_device(self, ptr, nbytes, stream=0):
+                words = self._view(ptr, nbytes // 4)
+                hdr = words[:HDR].view(np.int32)
+                if hdr[0] != MAGIC or hdr[1] != 2 or hdr[2] != 0:
+                    self.overflows = getattr(self, "overflows", 0) + 1
+                    return
+                o = HDR
+                for l in range(2):
+                    x0, y0, x1, y1 = (int(v) for v in hdr[4 + 4 * l: 8 + 4 * l])
+                    if x1 >= x0:
+                        n = (x1 - x0 + 1) * (y1 - y0 + 1)
+                        self.planes[l][y0:y1 + 1, x0:x1 + 1] = words[o:o + n].reshape(y1 - y0 + 1, x1 - x0 + 1)
+                        o += n
+
         fr = FakeRep()
         if rank == 0:
             fr.write(0, 3, 4, 10, 9, 1.5)      # level 1 stays clean on purpose
@@ -117,6 +154,27 @@ def _worker(rank, world, port, q):
         shipped = parallel.broadcast_dirty_tiles(fr, "cpu", src=0)
         ok = ok and shipped == 10 + 8 and float(fr.planes[1].sum()) == -8.0 and float(fr.planes[0][0:2, 0:5].sum()) == 20.0
         ok = ok and parallel.broadcast_dirty_tiles(fr, "cpu", src=0) == 0   # nothing dirty: nothing shipped
+        # one-shot protocol over the same transport: one fixed-size broadcast, no sizes through the hosts
+        buf = torch.zeros(64 + 200, dtype=torch.float32)
+        if rank == 0:
+            fr.write(0, 5, 5, 9, 7, 3.0)
+            fr.write(1, 0, 1, 1, 2, -2.0)
+        parallel.broadcast_dirty_tiles_async(fr, buf, src=0)
+        ok = ok and float(fr.planes[0][5:8, 5:10].sum()) == 45.0 and float(fr.planes[1][1:3, 0:2].sum()) == -8.0
+        ok = ok and (rank != 0 or fr.dirty == [None, None])
+        parallel.broadcast_dirty_tiles_async(fr, buf, src=0)               # nothing dirty: header only, planes unchanged
+        ok = ok and float(fr.planes[0][5:8, 5:10].sum()) == 45.0
+        # a dirty area larger than the buffer: nothing is shipped, the owner keeps its rectangles, replicas count it
+        before = fr.planes[0].copy()
+        if rank == 0:
+            fr.write(0, 0, 0, 31, 31, 7.0)                                  # 1024 cells > 200
+        parallel.broadcast_dirty_tiles_async(fr, buf, src=0)
+        if rank == 0:
+            ok = ok and fr.dirty[0] == (0, 0, 31, 31)
+        else:
+            ok = ok and getattr(fr, "overflows", 0) == 1 and bool(np.array_equal(fr.planes[0], before))
+        shipped = parallel.broadcast_dirty_tiles(fr, "cpu", src=0)          # ... and the two-step protocol catches up
+        ok = ok and shipped == 1024 and float(fr.planes[0].sum()) == 7.0 * 1024
         lo, hi = parallel.shard_range(K, rank, world)
         q.put((rank, ok, (lo, hi)))
     finally:
