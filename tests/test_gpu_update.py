@@ -93,6 +93,32 @@ def test_single_level_update_against_oracle(hsb_lib, pyoracle, oracle_kinds, mod
     orc.close()
 
 
+def test_update_by_long_scans(hsb_lib, pyoracle, oracle_kinds):
+    """Scans with more beams than one wave of the mark grid holds (the grid is capped at the resident CTAs, a team then
+    walks several beams): 5405 and 21 620 endpoints per updateByScan on a 3-level map, planes against the oracle."""
+    from hector_slam_b200 import capi, synth
+
+    kind = "reference" if "reference" in oracle_kinds else "port"
+    world = synth.World(1, seed=6)
+    orc = pyoracle.Oracle(kind, 0.05, 1024, 3)
+    orc.set_update_factors(0.4, 0.9)
+    rep = capi.MapRepB200(0.05, 1024, levels=3, update_factor_free=0.4, update_factor_occupied=0.9)
+    rng = np.random.default_rng(9)
+    poses = world.sample_free_poses(6, rng)
+    for k, p in enumerate(poses):
+        reps = 5 if k % 2 == 0 else 20
+        scan = np.concatenate([synth.make_scan(world, p, np.random.default_rng(100 * k + r)) for r in range(reps)])
+        pw = p.astype(np.float32)
+        orc.match(pw, scan)                    # fills the coarse-level containers on both sides (MapRepMultiMap.h:127)
+        rep.matchData(pw, scan)
+        orc.update_by_scan(scan, pw)
+        rep.updateByScan(scan, pw)
+    for l in range(3):
+        compare_planes(rep.download_level(l), orc.get_logodds(l), f"long scans level {l}")
+    rep.close()
+    orc.close()
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_slam_run(hsb_lib, mode):
     """The HectorSlamProcessor::update sequence (match -> gate -> updateByScan -> onMapUpdated)
